@@ -1,0 +1,105 @@
+"""TEST INFRASTRUCTURE ONLY -- run the UNMODIFIED reference (`/root/reference/*.py`) on CPU through
+the DGL stand-in in `oracle/dgl`, and write same-schema synthetic `.mat` datasets for it.
+
+Only usable where `/root/reference` exists (the build container). It is used by
+`tests/golden/make_golden.py` to freeze golden vectors and by the `not gpu` tests that validate
+`oracle/restate.py` against the live reference; nothing that runs on the GPU box imports it.
+
+`.mat` schema follows README.md:76-83 and data_loader.py:110-129: `didr` [N_dis x N_drug],
+`drug` [N_drug x N_drug], `disease` [N_dis x N_dis], `drug_embed` [N_drug x F],
+`disease_embed` [N_dis x F], `Wrname` [N_drug x 1] object array.
+"""
+import contextlib
+import importlib
+import io
+import os
+import sys
+
+import numpy as np
+
+REFERENCE_DIR = os.environ.get('DREAMGNN_REFERENCE_DIR', '/root/reference')
+ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+_REF_MODULES = ('utils', 'augmentation', 'data_loader', 'layers', 'model', 'evaluation', 'train')
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_DIR, 'layers.py'))
+
+
+def import_reference(quiet=True):
+    """Return a dict {name: module} of the reference's modules, imported unmodified."""
+    if not reference_available():
+        raise RuntimeError('reference sources not present at %s' % REFERENCE_DIR)
+    for p in (REFERENCE_DIR, ORACLE_DIR):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, REFERENCE_DIR)
+    sys.path.insert(0, ORACLE_DIR)        # `import dgl` -> oracle/dgl
+    mods = {}
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink if quiet else sys.stdout):
+        for name in _REF_MODULES:
+            m = sys.modules.get(name)
+            if m is None or not getattr(m, '__file__', '').startswith(REFERENCE_DIR):
+                sys.modules.pop(name, None)
+                m = importlib.import_module(name)
+            mods[name] = m
+    return mods
+
+
+def synthetic_mat_arrays(n_drug, n_dis, n_pos, embed_dim=768, sim_rank=32, seed=0):
+    """Seeded synthetic dataset (SURVEY.md 8d config 1 generator)."""
+    rng = np.random.default_rng(seed)
+    ed_drug, ed_dis = embed_dim if isinstance(embed_dim, (tuple, list)) else (embed_dim, embed_dim)
+    cells = rng.choice(n_drug * n_dis, size=n_pos, replace=False)
+    assoc = np.zeros((n_drug, n_dis), dtype=np.float64)
+    assoc[cells // n_dis, cells % n_dis] = 1.0
+
+    def sim(n):
+        x = rng.standard_normal((n, sim_rank))
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        s = (x @ x.T + 1.0) / 2.0
+        np.fill_diagonal(s, 1.0)
+        return s
+
+    names = np.empty((n_drug, 1), dtype=object)
+    for i in range(n_drug):
+        names[i, 0] = np.array(['DB%05d' % i])
+    return {
+        'didr': assoc.T.copy(),
+        'drug': sim(n_drug),
+        'disease': sim(n_dis),
+        'drug_embed': rng.standard_normal((n_drug, ed_drug)),
+        'disease_embed': rng.standard_normal((n_dis, ed_dis)),
+        'Wrname': names,
+    }
+
+
+def write_synthetic_mat(root, name, **kw):
+    """Write `<root>/raw_data/drug_data/<name>/<name>.mat` (data_loader.py:33-38 relative paths)."""
+    import scipy.io as sio
+    d = os.path.join(root, 'raw_data', 'drug_data', name)
+    os.makedirs(d, exist_ok=True)
+    arrays = synthetic_mat_arrays(**kw)
+    sio.savemat(os.path.join(d, name + '.mat'), arrays)
+    return arrays
+
+
+@contextlib.contextmanager
+def chdir(path):
+    old = os.getcwd()
+    os.chdir(path)
+    try:
+        yield
+    finally:
+        os.chdir(old)
+
+
+def load_reference_dataset(root, name, k=4, quiet=True):
+    """Instantiate the reference's DrugDataLoader on a synthetic `.mat` under `root`."""
+    import torch as th
+    mods = import_reference(quiet)
+    sink = io.StringIO()
+    with chdir(root), contextlib.redirect_stdout(sink if quiet else sys.stdout):
+        ds = mods['data_loader'].DrugDataLoader(name, th.device('cpu'), symm=True, k=k)
+    return mods, ds
