@@ -1,0 +1,112 @@
+// Shared helpers for libdreamgnn.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dreamgnn.h"
+
+namespace dg {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+inline cudaStream_t as_stream(dg_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Every launcher ends with this: counts the launch and turns a launch error into a return code.
+#define DG_CHECK_LAUNCH(name)                                                   \
+  do {                                                                          \
+    ::dg::count_launch();                                                       \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      ::dg::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return static_cast<int>(e__);                                             \
+    }                                                                           \
+  } while (0)
+
+#define DG_CHECK_CUDA(call)                                                         \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ::dg::set_error("%s failed: %s", #call, cudaGetErrorString(e__));             \
+      return static_cast<int>(e__);                                                 \
+    }                                                                               \
+  } while (0)
+
+#define DG_REQUIRE(cond, msg)                                   \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      ::dg::set_error("%s: %s", __func__, msg);                 \
+      return DG_ERR_INVALID_ARGUMENT;                           \
+    }                                                           \
+  } while (0)
+
+#define DG_PROPAGATE(call)      \
+  do {                          \
+    int rc__ = (call);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Workspace {
+  char* base;
+  size_t size, off;
+  Workspace(void* p, size_t n) : base(static_cast<char*>(p)), size(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t o = align_up(off, 256);
+    size_t end = o + count * sizeof(T);
+    if (end > size || base == nullptr) return nullptr;
+    off = end;
+    return reinterpret_cast<T*>(base + o);
+  }
+};
+inline size_t ws_add(size_t acc, size_t bytes) { return align_up(acc, 256) + bytes; }
+
+// 148 SMs on B200; grids for grid-stride kernels are sized as a multiple of this.
+constexpr int kNumSM = 148;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// Streaming 128-bit loads/stores that do not allocate in L1 (gathered rows are not re-used by the
+// same SM; index arrays are read once).
+__device__ __forceinline__ float4 ldg_f4_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_u4_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ldg_i32_stream(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// Counter-based dropout generator shared by forward and backward kernels: the keep decision for
+// element (a, b) under `seed` is a pure function, so the backward regenerates the forward's mask.
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return static_cast<uint32_t>(x);
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t a, uint32_t b, uint32_t thresh) {
+  // keep with probability 1-p: thresh = floor(p * 2^32)
+  uint64_t x = seed ^ (a * 0x9e3779b97f4a7c15ULL) ^ (static_cast<uint64_t>(b) << 40);
+  return mix32(x + 0x632be59bd9b4e019ULL) >= thresh;
+}
+
+}  // namespace dg
