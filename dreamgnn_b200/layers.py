@@ -1,0 +1,370 @@
+"""Drop-in mirrors of the reference's `layers.py` modules (same constructor arguments, forward
+signatures, parameter names / state_dict keys, initialisation order) running on the sm_100a kernels
+behind `dreamgnn_b200.ops`. Citations are into /root/reference/layers.py.
+
+What changes underneath:
+  * GCMCLayer (layers.py:18-143): one projection GEMM per node type produces the messages of all R
+    relations side by side ([N_src, R*D]); one SpMM launch per destination type walks the combined
+    relation-block CSR with `dropout(cj)[src]` and `ci[dst]` fused, i.e. HeteroGraphConv's
+    per-etype update_all + stack/sum (K2-K6 in SURVEY.md) become GEMM + SpMM. Backward is the same
+    SpMM on the transposed block -- deterministic, no atomics.
+  * GCN / FGCN (layers.py:238-285): `x @ W` is computed once and reused for the similarity and the
+    feature graph; spmm + bias (+ReLU) run in one kernel on a cached CSR of the COO adjacency.
+  * MLPDecoder (layers.py:341-379): exact split of lin1 over the concat + fused gather/MLP kernel.
+The per-relation `GCMCGraphConv.forward` / `HeteroGraphConv.forward` entry points stay available.
+"""
+import math
+
+import torch as th
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import init
+from torch.nn.parameter import Parameter
+
+from . import ops
+from .graph import DGLError
+from .utils import get_activation, to_etype_name
+
+# feature storage for the gathered GCMC messages: th.float32 (1e-5 parity path) or th.bfloat16
+# (2e-2 path: bf16 storage, fp32 accumulate)
+MESSAGE_DTYPE = th.float32
+
+
+def _pad_cols(t, mult):
+    pad = (-t.shape[-1]) % mult
+    return F.pad(t, (0, pad)) if pad else t
+
+
+def _flat_f32(t):
+    return t.reshape(-1).to(th.float32).contiguous()
+
+
+def adjacency_csr(adj):
+    """CSR sidecar of a torch sparse-COO adjacency (cached on the tensor object). The COO may be
+    uncoalesced (augmentation.py:124): duplicates simply stay separate entries of the row."""
+    csr = getattr(adj, '_dg_csr', None)
+    if csr is None:
+        if not (isinstance(adj, th.Tensor) and adj.is_sparse):
+            raise TypeError('adjacency must be a torch sparse COO tensor')
+        if not adj.is_cuda:
+            raise RuntimeError('GraphConvolution needs CUDA tensors (no CPU fallback)')
+        idx = adj._indices()
+        csr = ops.CSR.from_coo(idx[0], idx[1], adj.shape[0], adj.shape[1], adj._values().to(th.float32))
+        adj._dg_csr = csr
+    return csr
+
+
+class HeteroGraphConv(nn.Module):
+    """Mirror of dgl.nn.pytorch.HeteroGraphConv as used at layers.py:98 / :129 (generic per-relation
+    loop; GCMCLayer.forward takes the fused relation-block path instead)."""
+
+    def __init__(self, mods, aggregate='sum'):
+        super().__init__()
+        self.mods = nn.ModuleDict(mods)
+        self.aggregate = aggregate
+
+    def forward(self, g, inputs, mod_args=None, mod_kwargs=None):
+        mod_args, mod_kwargs = mod_args or {}, mod_kwargs or {}
+        outputs = {nt: [] for nt in g.dsttypes}
+        for stype, etype, dtype in g.canonical_etypes:
+            if stype not in inputs:
+                continue
+            out = self.mods[etype](g[stype, etype, dtype], (inputs[stype], inputs[dtype]),
+                                   *mod_args.get(etype, ()), **mod_kwargs.get(etype, {}))
+            outputs[dtype].append(out)
+        rsts = {}
+        for nt, alist in outputs.items():
+            if alist:
+                rsts[nt] = th.stack(alist, dim=0).sum(0) if self.aggregate == 'sum' else th.stack(alist, dim=1)
+        return rsts
+
+
+class GCMCGraphConv(nn.Module):
+    """layers.py:146-236."""
+
+    def __init__(self, in_feats, out_feats, weight=True, device=None, dropout_rate=0.1):
+        super().__init__()
+        self._in_feats, self._out_feats, self.device = in_feats, out_feats, device
+        self.dropout = nn.Dropout(dropout_rate)
+        if weight:
+            self.weight = nn.Parameter(th.Tensor(in_feats, out_feats))
+        else:
+            self.register_parameter('weight', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.weight is not None:
+            init.xavier_uniform_(self.weight)
+
+    def forward(self, graph, feat, weight=None, Two_Stage=False):
+        with graph.local_scope():
+            if isinstance(feat, tuple):
+                feat, _ = feat
+            cj, ci = graph.srcdata['cj'], graph.dstdata['ci']
+            if feat.size(0) != graph.number_of_src_nodes():
+                raise ValueError('feat has %d rows for %d source nodes' % (feat.size(0), graph.number_of_src_nodes()))
+            if weight is not None:
+                if self.weight is not None:
+                    raise DGLError('External weight provided but module also has its own weight parameter, '
+                                   'please set weight=False.')
+            else:
+                weight = self.weight
+            if weight is not None:
+                feat = dot_or_identity(feat, weight, self.device)
+            d = feat.shape[1]
+            rst = ops.spmm(graph.etype_csr(), _pad_cols(feat, 4), src_scale=_flat_f32(self.dropout(cj)),
+                           dst_scale=_flat_f32(ci))
+        return rst[:, :d]
+
+
+class GCMCLayer(nn.Module):
+    """layers.py:18-143."""
+
+    def __init__(self, rating_vals, user_in_units, movie_in_units, msg_units, out_units, dropout_rate=0.1,
+                 agg='stack', agg_act=None, ini=True, share_user_item_param=False, basis_units=2, device=None):
+        super().__init__()
+        self.rating_vals = rating_vals
+        self.agg = agg
+        self.share_user_item_param = share_user_item_param
+        self.user_in_units = user_in_units
+        effective = msg_units
+        if agg == 'stack':
+            assert effective % len(rating_vals) == 0
+            effective = effective // len(rating_vals)
+        if ini:
+            effective = effective // 3
+        self.msg_units = effective
+        self.ufc = nn.Linear(effective, out_units)
+        self.ifc = self.ufc if share_user_item_param else nn.Linear(effective, out_units)
+        self.dropout = nn.Dropout(dropout_rate)
+        self.W_r = {}
+        self.basis_units = basis_units
+        self.att = nn.Parameter(th.randn(len(self.rating_vals), basis_units))
+        self.basis = nn.Parameter(th.randn(basis_units, user_in_units, effective))
+        sub = {}
+        shared_dims = share_user_item_param and user_in_units == movie_in_units
+        for rating in rating_vals:
+            rating = to_etype_name(rating)
+            if shared_dims:
+                sub[rating] = GCMCGraphConv(user_in_units, effective, False, device, dropout_rate)
+                sub['rev-%s' % rating] = GCMCGraphConv(user_in_units, effective, False, device, dropout_rate)
+            else:
+                self.W_r = None
+                sub[rating] = GCMCGraphConv(user_in_units, effective, True, device, dropout_rate)
+                sub['rev-%s' % rating] = GCMCGraphConv(movie_in_units, effective, True, device, dropout_rate)
+        self.conv = HeteroGraphConv(sub, aggregate=agg)
+        self.agg_act = get_activation(agg_act)
+        self.device = device
+        self.reset_parameters()
+
+    def partial_to(self, device):
+        assert device == self.device
+        if device is not None:
+            self.ufc.cuda(device)
+            if not self.share_user_item_param:
+                self.ifc.cuda(device)
+            self.dropout.cuda(device)
+
+    def reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def _relation_weights(self):
+        """etype -> [in, msg] weight: W = att @ basis for the shared-dims branch (layers.py:120-127),
+        the per-relation module's own parameter otherwise (layers.py:86-97)."""
+        if self.W_r is None:
+            return {et: m.weight for et, m in self.conv.mods.items()}
+        W = th.matmul(self.att, self.basis.view(self.basis_units, -1)).view(-1, self.user_in_units, self.msg_units)
+        self.W = W
+        out = {}
+        for i, rating in enumerate(self.rating_vals):
+            rating = to_etype_name(rating)
+            out[rating] = W[i]
+            out['rev-%s' % rating] = W[i]
+        return out
+
+    def forward(self, graph, drug_feat=None, dis_feat=None, Two_Stage=False):
+        if self.agg != 'sum':
+            raise NotImplementedError("only agg='sum' is usable downstream (as in the reference)")
+        feats = {'drug': drug_feat, 'disease': dis_feat}
+        weights = self._relation_weights()
+        D = self.msg_units
+        mult = 8 if MESSAGE_DTYPE == th.bfloat16 else 4
+        out = {}
+        seen = []
+        for c in graph.canonical_etypes:                 # blocks in the reference's etype order
+            if c[2] not in seen:
+                seen.append(c[2])
+        for dst_type in seen:
+            blk = graph.block(dst_type)
+            x = feats[blk.src_type]
+            if x.size(0) != blk.n_src:
+                raise ValueError('%s features have %d rows for %d nodes' % (blk.src_type, x.size(0), blk.n_src))
+            wcat = th.cat([_pad_cols(weights[c[1]], mult) for c in blk.etypes], dim=1)      # [in, R*Dp]
+            h = th.mm(x, wcat)                                                              # all relations at once
+            dp = wcat.shape[1] // blk.num_rel
+            cj = graph.nodes[blk.src_type].data['cj']
+            scale = th.stack([_flat_f32(self.conv.mods[c[1]].dropout(cj)) for c in blk.etypes], dim=1).reshape(-1)
+            if MESSAGE_DTYPE != th.float32:
+                h = h.to(MESSAGE_DTYPE)
+            agg = ops.spmm(blk.csr, h.view(blk.n_src * blk.num_rel, dp), src_scale=scale,
+                           dst_scale=_flat_f32(graph.nodes[dst_type].data['ci']))
+            out[dst_type] = agg[:, :D] if dp != D else agg
+        drug = self.dropout(self.agg_act(out['drug']))
+        dis = self.dropout(self.agg_act(out['disease']))
+        return self.ifc(drug), self.ufc(dis)
+
+
+class GraphConvolution(nn.Module):
+    """layers.py:287-321."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = Parameter(th.FloatTensor(in_features, out_features))
+        if bias:
+            self.bias = Parameter(th.FloatTensor(out_features))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1. / math.sqrt(self.weight.size(1))
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def support(self, input):
+        return th.mm(input, self.weight)
+
+    def aggregate(self, support, adj, relu=False):
+        d = support.shape[1]
+        bias = self.bias
+        if d % 4:
+            support = _pad_cols(support, 4)
+            bias = _pad_cols(bias, 4) if bias is not None else None
+        out = ops.spmm(adjacency_csr(adj), support, bias=bias, relu=relu)
+        return out[:, :d] if out.shape[1] != d else out
+
+    def forward(self, input, adj):
+        if adj.device != input.device:
+            adj = adj.to(input.device)
+        return self.aggregate(self.support(input), adj)
+
+    def __repr__(self):
+        return '%s (%d -> %d)' % (self.__class__.__name__, self.in_features, self.out_features)
+
+
+class GCN(nn.Module):
+    """layers.py:238-249."""
+
+    def __init__(self, features, nhid, nhid2, dropout):
+        super().__init__()
+        self.gc1 = GraphConvolution(features, nhid)
+        self.gc2 = GraphConvolution(nhid, nhid2)
+        self.dropout = dropout
+
+    def _tail(self, support1, adj):
+        x = self.gc1.aggregate(support1, adj, relu=True)          # spmm + bias + ReLU in one kernel
+        x = F.dropout(x, self.dropout, training=self.training)
+        return self.gc2(x, adj)
+
+    def forward(self, x, adj):
+        return self._tail(self.gc1.support(x), adj)
+
+    def forward_shared(self, x, adjs):
+        """Same layer on several graphs over the same input: x @ W1 is computed once (the reference
+        recomputes it per graph, layers.py:263-270)."""
+        s1 = self.gc1.support(x)
+        return [self._tail(s1, adj) for adj in adjs]
+
+
+class FGCN(nn.Module):
+    """layers.py:251-285."""
+
+    def __init__(self, fdim_drug, fdim_disease, nhid1, nhid2, dropout):
+        super().__init__()
+        self.FGCN_drug = GCN(fdim_drug, nhid1, nhid2, dropout)
+        self.FGCN_disease = GCN(fdim_disease, nhid1, nhid2, dropout)
+        self.dropout = dropout
+        self.drug_fusion = nn.Linear(nhid2 * 2, nhid2)
+        self.disease_fusion = nn.Linear(nhid2 * 2, nhid2)
+
+    def forward(self, drug_graph, drug_sim_feat, dis_graph, disease_sim_feat,
+                drug_feature_graph=None, disease_feature_graph=None):
+        if drug_feature_graph is None or disease_feature_graph is None:
+            emb1_sim = self.FGCN_drug(drug_sim_feat, drug_graph)
+            emb2_sim = self.FGCN_disease(disease_sim_feat, dis_graph)
+            return emb1_sim, emb2_sim, emb1_sim, None, emb2_sim, None
+        if self.training and self.dropout > 0:
+            # keep the reference's dropout draw order: drug(sim), disease(sim), drug(feat), disease(feat)
+            s_d, s_s = self.FGCN_drug.gc1.support(drug_sim_feat), self.FGCN_disease.gc1.support(disease_sim_feat)
+            emb1_sim = self.FGCN_drug._tail(s_d, drug_graph)
+            emb2_sim = self.FGCN_disease._tail(s_s, dis_graph)
+            emb1_feat = self.FGCN_drug._tail(s_d, drug_feature_graph)
+            emb2_feat = self.FGCN_disease._tail(s_s, disease_feature_graph)
+        else:
+            emb1_sim, emb1_feat = self.FGCN_drug.forward_shared(drug_sim_feat, [drug_graph, drug_feature_graph])
+            emb2_sim, emb2_feat = self.FGCN_disease.forward_shared(disease_sim_feat, [dis_graph, disease_feature_graph])
+        fused_drug = th.relu(self.drug_fusion(th.cat([emb1_sim, emb1_feat], dim=1)))
+        fused_disease = th.relu(self.disease_fusion(th.cat([emb2_sim, emb2_feat], dim=1)))
+        emb1 = F.dropout(fused_drug, p=self.dropout, training=self.training)
+        emb2 = F.dropout(fused_disease, p=self.dropout, training=self.training)
+        return emb1, emb2, emb1_sim, emb1_feat, emb2_sim, emb2_feat
+
+
+class Attention(nn.Module):
+    """layers.py:324-338."""
+
+    def __init__(self, in_size, hidden_size=16, dropout_rate=0.1):
+        super().__init__()
+        self.project = nn.Sequential(nn.Linear(in_size, hidden_size), nn.Tanh(), nn.Linear(hidden_size, 1, bias=False))
+        self.dropout = nn.Dropout(dropout_rate)
+
+    def forward(self, z):
+        beta = self.dropout(th.softmax(self.project(z), dim=1))
+        return (beta * z).sum(1), beta
+
+
+class MLPDecoder(nn.Module):
+    """layers.py:341-379."""
+
+    def __init__(self, in_units, dropout_rate=0.1):
+        super().__init__()
+        self.dropout = nn.Dropout(dropout_rate)
+        self.sigmoid = nn.Sigmoid()
+        self.lin1 = nn.Linear(2 * in_units, 128)
+        self.lin2 = nn.Linear(128, 64)
+        self.lin3 = nn.Linear(64, 1)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+        self.lin3.reset_parameters()
+
+    def forward(self, graph, drug_feat, dis_feat):
+        pairs = graph.pair_graph()
+        n_in = drug_feat.shape[1]
+        w1 = self.lin1.weight
+        pd = F.linear(drug_feat, w1[:, :n_in], self.lin1.bias)     # drug half of lin1 (+ bias)
+        ps = F.linear(dis_feat, w1[:, n_in:])                      # disease half
+        seed = int(th.randint(0, 2 ** 62, (1,)).item()) if self.training and self.dropout.p > 0 else 0
+        return ops.decoder_mlp(pd, ps, self.lin2.weight, self.lin2.bias, self.lin3.weight, self.lin3.bias, pairs,
+                               p=self.dropout.p, seed=seed, training=self.training)
+
+
+def udf_u_mul_e(edges):
+    """layers.py:378-379 (kept for API compatibility with graph.apply_edges)."""
+    return {'m': th.cat([edges.src['h'], edges.dst['h']], 1)}
+
+
+def dot_or_identity(A, B, device=None):
+    """layers.py:382-392."""
+    if A is None:
+        return B
+    if A.shape[1] == 3:
+        out = th.cat([B[A[:, 0].long()], B[A[:, 1].long()], B[A[:, 2].long()]], 1)
+        return out if device is None else out.to(device)
+    return th.matmul(A, B)

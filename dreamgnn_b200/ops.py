@@ -1,0 +1,343 @@
+"""Tensor-level wrappers over the C ABI (include/dreamgnn.h) and the autograd Functions built on
+them. Everything here requires CUDA tensors; there is no CPU fallback.
+
+Reference call sites replaced (citations into /root/reference):
+  * `CSR.from_coo` / `CSR.transpose`   DGL's lazy COO->CSC/CSR inside update_all (layers.py:229-232)
+  * `spmm` / `SpMMFunction`            update_all(copy_u,sum) with cj/ci fused (layers.py:224-234) and
+                                       th.spmm(adj, support)+bias (layers.py:312-314); backward = same
+                                       kernel on the transposed CSR, atomic-free
+  * `decoder_mlp` / `DecoderFunction`  apply_edges(udf_u_mul_e) + lin1/lin2/lin3 (layers.py:360-379)
+  * `csr_dropout`                      th.randperm edge dropout + graph rebuild (augmentation.py:35-124)
+  * `topk_rows`, `knn_graph_from_neighbors`   np.argpartition + scipy A+A^T+I, D^-1 A (data_loader.py:291-308)
+"""
+import torch as th
+
+from . import _lib as L
+
+I32 = th.int32
+DEC_H1, DEC_H2 = 128, 64
+SPMM_ACCUMULATE, SPMM_RELU = 1, 2
+
+
+def _i32(t, name):
+    """Narrow an index tensor to int32 with a range check (int64 accepted at the Python boundary)."""
+    if t.dtype == I32:
+        return t.contiguous()
+    if t.dtype != th.int64:
+        raise TypeError('%s must be int32 or int64' % name)
+    if t.numel() and (int(t.max()) > 0x7fffffff or int(t.min()) < 0):
+        raise ValueError('%s out of int32 range' % name)
+    return t.to(I32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# index primitives
+# ------------------------------------------------------------------------------------------------
+def exclusive_scan_i32(x):
+    lib = L.load()
+    n = x.numel()
+    out = th.empty(n + 1, dtype=I32, device=x.device)
+    ws = L.workspace(lib.dg_scan_workspace_bytes(n), x.device)
+    L.check(lib.dg_exclusive_scan_i32(L.ptr(x, I32, 'x'), L.ptr(out), n, L.ptr(ws), ws.numel(), L.stream()), 'scan')
+    return out
+
+
+def sort_pairs_u64(keys, vals, key_bits):
+    """Stable sort of int64-stored unsigned keys (+ optional int32 payload). Inputs are clobbered."""
+    lib = L.load()
+    n = keys.numel()
+    keys_out = th.empty_like(keys)
+    vals_out = th.empty_like(vals) if vals is not None else None
+    ws = L.workspace(lib.dg_sort_workspace_bytes(n), keys.device)
+    L.check(lib.dg_sort_pairs_u64(L.ptr(keys, th.int64, 'keys'), L.ptr(vals, I32 if vals is not None else None),
+                                  L.ptr(keys_out), L.ptr(vals_out), n, int(key_bits), L.ptr(ws), ws.numel(),
+                                  L.stream()), 'sort_pairs')
+    return keys_out, vals_out
+
+
+# ------------------------------------------------------------------------------------------------
+# CSR container
+# ------------------------------------------------------------------------------------------------
+class CSR:
+    """Canonical CSR (rows ascending, columns ascending inside a row) on device, int32.
+
+    `eid[s]` is the id of the edge stored in slot s -- ids refer to the COO list the *base* graph was
+    built from, and survive transposition and dropout compaction, so forward / transposed / dropped
+    variants of one graph stay consistent.
+    """
+
+    __slots__ = ('indptr', 'indices', 'eid', 'vals', 'n_rows', 'n_cols', '_t', 'slot_order')
+
+    def __init__(self, indptr, indices, eid, vals, n_rows, n_cols):
+        self.indptr, self.indices, self.eid, self.vals = indptr, indices, eid, vals
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self._t = None
+        self.slot_order = False     # True when the owning COO tensor lists its entries in slot order
+
+    @property
+    def nnz(self):
+        return int(self.indices.numel())
+
+    @property
+    def device(self):
+        return self.indptr.device
+
+    @staticmethod
+    def from_coo(row, col, n_rows, n_cols, vals=None, edge_ids=None):
+        lib = L.load()
+        row, col = _i32(row, 'row'), _i32(col, 'col')
+        if row.numel() and (int(row.max()) >= n_rows or int(col.max()) >= n_cols):
+            raise ValueError('edge endpoint out of range')
+        n = row.numel()
+        dev = row.device
+        indptr = th.empty(n_rows + 1, dtype=I32, device=dev)
+        indices = th.empty(n, dtype=I32, device=dev)
+        eid = th.empty(n, dtype=I32, device=dev)
+        ws = L.workspace(lib.dg_csr_build_workspace_bytes(n, n_rows), dev)
+        L.check(lib.dg_csr_build(L.ptr(row, I32, 'row'), L.ptr(col, I32, 'col'), n, n_rows, n_cols, L.ptr(indptr),
+                                 L.ptr(indices), L.ptr(eid), L.ptr(ws), ws.numel(), L.stream()), 'csr_build')
+        v = None
+        if vals is not None:
+            v = vals.contiguous()[eid.long()]
+        if edge_ids is not None:
+            eid = _i32(edge_ids, 'edge_ids')[eid.long()]
+        return CSR(indptr, indices, eid, v, n_rows, n_cols)
+
+    def rows(self):
+        """COO row id of every slot."""
+        lib = L.load()
+        out = th.empty(self.nnz, dtype=I32, device=self.device)
+        L.check(lib.dg_csr_expand_rows(L.ptr(self.indptr), self.n_rows, L.ptr(out), L.stream()), 'expand_rows')
+        return out
+
+    def transpose(self):
+        """Cached canonical CSR of the transposed matrix, carrying edge ids and values along."""
+        if self._t is None:
+            t = CSR.from_coo(self.indices, self.rows(), self.n_cols, self.n_rows, self.vals, self.eid)
+            t._t = self
+            self._t = t
+        return self._t
+
+    def degrees(self):
+        return (self.indptr[1:] - self.indptr[:-1])
+
+    def degree_norm(self):
+        """1/sqrt(degree) with 0 -> 0 (data_loader.py:454-457), fp32 [n_rows]."""
+        lib = L.load()
+        out = th.empty(self.n_rows, dtype=th.float32, device=self.device)
+        L.check(lib.dg_degree_norm(L.ptr(self.indptr), self.n_rows, L.ptr(out), L.stream()), 'degree_norm')
+        return out
+
+
+def keep_flags(n_edges, perms, device):
+    """uint8 keep flag per edge id: perms = [(perm int64, num_keep, id offset), ...]
+    (augmentation.py:48-52: keep the first num_keep entries of each randperm)."""
+    lib = L.load()
+    flags = th.zeros(n_edges, dtype=th.uint8, device=device)
+    for perm, num_keep, offset in perms:
+        L.check(lib.dg_keep_flags_from_perm(L.ptr(perm, th.int64, 'perm'), int(num_keep), int(offset), L.ptr(flags),
+                                            L.stream()), 'keep_flags')
+    return flags
+
+
+def csr_compact(csr, flags, n_keep):
+    """Order-preserving compaction of `csr` to the edges whose flag (by edge id) is set."""
+    lib = L.load()
+    dev = csr.device
+    indptr = th.empty(csr.n_rows + 1, dtype=I32, device=dev)
+    indices = th.empty(n_keep, dtype=I32, device=dev)
+    eid = th.empty(n_keep, dtype=I32, device=dev)
+    vals = th.empty(n_keep, dtype=th.float32, device=dev) if csr.vals is not None else None
+    ws = L.workspace(lib.dg_csr_compact_workspace_bytes(csr.n_rows), dev)
+    L.check(lib.dg_csr_compact(L.ptr(csr.indptr), L.ptr(csr.indices), L.ptr(csr.eid), L.ptr(csr.vals), csr.n_rows,
+                               L.ptr(flags, th.uint8, 'flags'), L.ptr(indptr), L.ptr(indices), L.ptr(eid),
+                               L.ptr(vals), L.ptr(ws), ws.numel(), L.stream()), 'csr_compact')
+    return CSR(indptr, indices, eid, vals, csr.n_rows, csr.n_cols)
+
+
+def csr_dropout(csr, flags, n_keep):
+    """Dropped graph in both orientations from one flag array (forward + transposed stay consistent)."""
+    fwd = csr_compact(csr, flags, n_keep)
+    bwd = csr_compact(csr.transpose(), flags, n_keep)
+    fwd._t, bwd._t = bwd, fwd
+    return fwd
+
+
+# ------------------------------------------------------------------------------------------------
+# SpMM
+# ------------------------------------------------------------------------------------------------
+def _spmm_raw(csr, x, src_scale=None, dst_scale=None, bias=None, flags=0, out=None):
+    lib = L.load()
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.contiguous()
+    if x.shape[0] != csr.n_cols:
+        raise ValueError('spmm: x has %d rows, graph has %d source nodes' % (x.shape[0], csr.n_cols))
+    d = x.shape[1]
+    if out is None:
+        out = th.empty((csr.n_rows, d), dtype=th.float32, device=x.device)
+    for nm, t, n in (('src_scale', src_scale, csr.n_cols), ('dst_scale', dst_scale, csr.n_rows), ('bias', bias, d)):
+        if t is not None and (t.numel() != n or t.dtype != th.float32):
+            raise ValueError('spmm: %s must be fp32 with %d elements' % (nm, n))
+    args = (L.ptr(csr.indptr), L.ptr(csr.indices), L.ptr(csr.vals), L.ptr(src_scale), L.ptr(dst_scale), L.ptr(bias))
+    if x.dtype == th.float32:
+        rc = lib.dg_spmm_csr_f32(*args, x.data_ptr() if x.is_cuda else L.ptr(x), x.stride(0), L.ptr(out),
+                                 out.stride(0), csr.n_rows, d, flags, L.stream())
+    elif x.dtype == th.bfloat16:
+        rc = lib.dg_spmm_csr_bf16(*args, x.data_ptr() if x.is_cuda else L.ptr(x), x.stride(0), L.ptr(out),
+                                  out.stride(0), csr.n_rows, d, flags, L.stream())
+    else:
+        raise TypeError('spmm: x must be float32 or bfloat16')
+    L.check(rc, 'spmm_csr')
+    return out
+
+
+class SpMMFunction(th.autograd.Function):
+    """out = act(dst_scale * (A_vals @ (src_scale * x)) + bias); grad flows to x and bias only."""
+
+    @staticmethod
+    def forward(ctx, x, bias, csr, src_scale, dst_scale, relu):
+        out = _spmm_raw(csr, x, src_scale, dst_scale, bias, SPMM_RELU if relu else 0)
+        ctx.csr, ctx.relu, ctx.has_bias = csr, relu, bias is not None
+        ctx.save_for_backward(src_scale, dst_scale, out if relu else None)
+        ctx.x_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        src_scale, dst_scale, out = ctx.saved_tensors
+        dout = dout.contiguous()
+        if ctx.relu:
+            dout = dout * (out > 0).to(dout.dtype)
+        dbias = dout.sum(0) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # d x[j] = src_scale[j] * sum_{i : j in row i} vals * dst_scale[i] * dout[i]  -> transposed CSR
+            dx = _spmm_raw(ctx.csr.transpose(), dout, dst_scale, src_scale, None, 0)
+            if ctx.x_dtype != th.float32:
+                dx = dx.to(ctx.x_dtype)
+        return dx, dbias, None, None, None, None
+
+
+def spmm(csr, x, src_scale=None, dst_scale=None, bias=None, relu=False):
+    if not x.is_cuda:
+        raise RuntimeError('dreamgnn_b200.spmm needs CUDA tensors (no CPU fallback)')
+    return SpMMFunction.apply(x, bias, csr, src_scale, dst_scale, relu)
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder
+# ------------------------------------------------------------------------------------------------
+class PairGraph:
+    """Scored (drug, disease) pairs in label order + the two segment structures the deterministic
+    backward needs (CSR by drug and by disease whose `indices` are pair ids)."""
+
+    def __init__(self, src, dst, n_src, n_dst):
+        self.src, self.dst = _i32(src, 'src'), _i32(dst, 'dst')
+        self.n_src, self.n_dst = int(n_src), int(n_dst)
+        self._by_src = self._by_dst = None
+
+    @property
+    def n_pairs(self):
+        return int(self.src.numel())
+
+    def _segments(self, key, n):
+        ids = th.arange(self.n_pairs, dtype=I32, device=key.device)
+        c = CSR.from_coo(key, ids, n, max(self.n_pairs, 1))
+        return c
+
+    def by_src(self):
+        if self._by_src is None:
+            self._by_src = self._segments(self.src, self.n_src)
+        return self._by_src
+
+    def by_dst(self):
+        if self._by_dst is None:
+            self._by_dst = self._segments(self.dst, self.n_dst)
+        return self._by_dst
+
+
+class DecoderFunction(th.autograd.Function):
+    @staticmethod
+    def forward(ctx, pd, ps, w2, b2, w3, b3, pairs, p, seed, save):
+        lib = L.load()
+        pd, ps, w2, b2, w3, b3 = (t.contiguous() for t in (pd, ps, w2, b2, w3, b3))
+        if pd.shape[1] != DEC_H1 or ps.shape[1] != DEC_H1 or tuple(w2.shape) != (DEC_H2, DEC_H1):
+            raise ValueError('decoder hidden widths are fixed at 128 / 64 (layers.py:349-351)')
+        if pd.shape[0] != pairs.n_src or ps.shape[0] != pairs.n_dst:
+            raise ValueError('decoder: node counts do not match the pair graph')
+        e = pairs.n_pairs
+        out = th.empty(e, dtype=th.float32, device=pd.device)
+        z2 = th.empty((e, DEC_H2), dtype=th.float32, device=pd.device) if save else None
+        L.check(lib.dg_decoder_fwd_f32(L.ptr(pairs.src), L.ptr(pairs.dst), e, L.ptr(pd, th.float32, 'pd'),
+                                       L.ptr(ps, th.float32, 'ps'), L.ptr(w2, th.float32), L.ptr(b2, th.float32),
+                                       L.ptr(w3, th.float32), L.ptr(b3, th.float32), float(p), int(seed), L.ptr(out),
+                                       L.ptr(z2), L.stream()), 'decoder_fwd')
+        ctx.pairs, ctx.p, ctx.seed = pairs, float(p), int(seed)
+        ctx.save_for_backward(pd, ps, w2, w3, z2)
+        return out.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        pd, ps, w2, w3, z2 = ctx.saved_tensors
+        if z2 is None:
+            raise RuntimeError('decoder forward was run without saving z2 (inference mode)')
+        pairs = ctx.pairs
+        e = pairs.n_pairs
+        dev = pd.device
+        dout = dout.reshape(-1).contiguous()
+        dz1 = th.empty((max(e, 1), DEC_H1), dtype=th.float32, device=dev)
+        dw2 = th.empty((DEC_H2, DEC_H1), dtype=th.float32, device=dev)
+        db2 = th.empty(DEC_H2, dtype=th.float32, device=dev)
+        dw3 = th.empty((1, DEC_H2), dtype=th.float32, device=dev)
+        db3 = th.empty(1, dtype=th.float32, device=dev)
+        ws = L.workspace(lib.dg_decoder_bwd_workspace_bytes(e), dev)
+        L.check(lib.dg_decoder_bwd_f32(L.ptr(pairs.src), L.ptr(pairs.dst), e, L.ptr(pd), L.ptr(ps), L.ptr(w2),
+                                       L.ptr(w3), ctx.p, ctx.seed, L.ptr(z2), L.ptr(dout, th.float32, 'dout'),
+                                       L.ptr(dz1), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3), L.ptr(ws),
+                                       ws.numel(), L.stream()), 'decoder_bwd')
+        # scatter of dz1 into node gradients = two segment sums in fixed order (no atomics)
+        dpd = _spmm_raw(pairs.by_src(), dz1) if ctx.needs_input_grad[0] else None
+        dps = _spmm_raw(pairs.by_dst(), dz1) if ctx.needs_input_grad[1] else None
+        return dpd, dps, dw2, db2, dw3, db3, None, None, None, None
+
+
+def decoder_mlp(pd, ps, w2, b2, w3, b3, pairs, p=0.0, seed=0, training=False):
+    if not pd.is_cuda:
+        raise RuntimeError('dreamgnn_b200.decoder_mlp needs CUDA tensors (no CPU fallback)')
+    save = th.is_grad_enabled() and any(t.requires_grad for t in (pd, ps, w2, b2, w3, b3))
+    return DecoderFunction.apply(pd, ps, w2, b2, w3.reshape(1, -1), b3, pairs, p if training else 0.0, seed, save)
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN graphs
+# ------------------------------------------------------------------------------------------------
+def topk_rows(sim, k):
+    """Row-wise top-k columns of a float64 block (value desc, column asc), returned ascending."""
+    lib = L.load()
+    if sim.dtype != th.float64 or sim.dim() != 2 or sim.stride(1) != 1:
+        raise TypeError('topk_rows: float64 row-major matrix expected')
+    out = th.empty((sim.shape[0], k), dtype=I32, device=sim.device)
+    L.check(lib.dg_topk_rows_f64(L.ptr(sim) if sim.is_contiguous() else sim.data_ptr(), sim.shape[0], sim.shape[1],
+                                 sim.stride(0), int(k), L.ptr(out), L.stream()), 'topk_rows')
+    return out
+
+
+def knn_graph_from_neighbors(nbr):
+    """[n,k] neighbour lists -> CSR of D^-1 (A + A^T + I) with fp32 values (row/col sorted)."""
+    lib = L.load()
+    nbr = _i32(nbr, 'nbr')
+    n, k = nbr.shape
+    dev = nbr.device
+    nnz_max = 2 * n * k + n
+    indptr = th.empty(n + 1, dtype=I32, device=dev)
+    row = th.empty(nnz_max, dtype=I32, device=dev)
+    col = th.empty(nnz_max, dtype=I32, device=dev)
+    val = th.empty(nnz_max, dtype=th.float32, device=dev)
+    nnz = th.zeros(1, dtype=I32, device=dev)
+    ws = L.workspace(lib.dg_knn_graph_workspace_bytes(n, k), dev)
+    L.check(lib.dg_knn_graph_from_neighbors(L.ptr(nbr), n, k, L.ptr(indptr), L.ptr(row), L.ptr(col), L.ptr(val),
+                                            L.ptr(nnz), L.ptr(ws), ws.numel(), L.stream()), 'knn_graph')
+    m = int(nnz.item())                      # one sync per graph build (not on the training path)
+    csr = CSR(indptr, col[:m].contiguous(), th.arange(m, dtype=I32, device=dev), val[:m].contiguous(), n, n)
+    return csr, row[:m].contiguous()

@@ -39,24 +39,31 @@ extern "C" {
 
 typedef void* dg_stream_t; /* cudaStream_t */
 
+/* exported with default visibility; everything else in the library is hidden */
+#if defined(__GNUC__)
+#define DG_API __attribute__((visibility("default")))
+#else
+#define DG_API
+#endif
+
 /* ---- library bookkeeping ------------------------------------------------------------------ */
-int dg_abi_version(void);
-const char* dg_last_error(void);
+DG_API int dg_abi_version(void);
+DG_API const char* dg_last_error(void);
 /* Number of kernels this library has launched since load / last reset (bench.py "gpu_launches"). */
-unsigned long long dg_launch_count(void);
-void dg_reset_launch_count(void);
+DG_API unsigned long long dg_launch_count(void);
+DG_API void dg_reset_launch_count(void);
 
 /* ---- index primitives ---------------------------------------------------------------------- */
 /* Exclusive prefix sum of n int32 values; out[n] (one past the end) receives the total, so `out`
  * must hold n+1 elements. in == out is allowed only if out is sized n+1 and in aliases out[0..n). */
-size_t dg_scan_workspace_bytes(int64_t n);
-int dg_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n,
+DG_API size_t dg_scan_workspace_bytes(int64_t n);
+DG_API int dg_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n,
                           void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
 /* Stable LSD radix sort of n (uint64 key, int32 value) pairs on the low `key_bits` bits.
  * Results land in keys_out / vals_out; keys_in / vals_in are clobbered. vals may be NULL. */
-size_t dg_sort_workspace_bytes(int64_t n);
-int dg_sort_pairs_u64(uint64_t* keys_in, int32_t* vals_in, uint64_t* keys_out, int32_t* vals_out,
+DG_API size_t dg_sort_workspace_bytes(int64_t n);
+DG_API int dg_sort_pairs_u64(uint64_t* keys_in, int32_t* vals_in, uint64_t* keys_out, int32_t* vals_out,
                       int64_t n, int key_bits, void* workspace, size_t workspace_bytes,
                       dg_stream_t stream);
 
@@ -67,33 +74,33 @@ int dg_sort_pairs_u64(uint64_t* keys_in, int32_t* vals_in, uint64_t* keys_out, i
  *   row/col [n_edges]; indptr [n_rows+1]; indices [n_edges]; eid [n_edges] = input position of the
  *   edge stored in each slot (the permutation edge values / transposes are carried with).
  * Deterministic: the result does not depend on the order of the input list. */
-size_t dg_csr_build_workspace_bytes(int64_t n_edges, int64_t n_rows);
-int dg_csr_build(const int32_t* row, const int32_t* col, int64_t n_edges, int64_t n_rows,
+DG_API size_t dg_csr_build_workspace_bytes(int64_t n_edges, int64_t n_rows);
+DG_API int dg_csr_build(const int32_t* row, const int32_t* col, int64_t n_edges, int64_t n_rows,
                  int64_t n_cols, int32_t* indptr, int32_t* indices, int32_t* eid,
                  void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
 /* norm[i] = 1/sqrt(indptr[i+1]-indptr[i]) as fp32 with degree 0 -> 0; bit-exact with
  * data_loader.py:454-457 (_calc_norm) when indptr is the CSR of all relations into node type i. */
-int dg_degree_norm(const int32_t* indptr, int64_t n_rows, float* norm, dg_stream_t stream);
+DG_API int dg_degree_norm(const int32_t* indptr, int64_t n_rows, float* norm, dg_stream_t stream);
 
 /* ---- per-iteration edge dropout rebuild (augmentation.py:13-124) --------------------------- */
 /* flags[offset + perm[i]] = 1 for i < num_keep: "keep edge e iff rank(e) < num_keep" with
  * num_keep = max(1, int(E*(1-rate))) evaluated by the caller (augmentation.py:48-52).
  * flags must be zeroed by the caller beforehand. perm is torch.randperm's int64 output. */
-int dg_keep_flags_from_perm(const int64_t* perm, int64_t num_keep, int64_t offset,
+DG_API int dg_keep_flags_from_perm(const int64_t* perm, int64_t num_keep, int64_t offset,
                             uint8_t* flags, dg_stream_t stream);
 
 /* Compact a canonical CSR to the edges whose flag (indexed by eid) is set, preserving order, so
  * the dropped graph's CSR is again canonical without a sort. vals / out_vals may be NULL.
  * out_indices / out_eid / out_vals must hold the number of kept edges (known to the caller). */
-size_t dg_csr_compact_workspace_bytes(int64_t n_rows);
-int dg_csr_compact(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
+DG_API size_t dg_csr_compact_workspace_bytes(int64_t n_rows);
+DG_API int dg_csr_compact(const int32_t* indptr, const int32_t* indices, const int32_t* eid,
                    const float* vals, int64_t n_rows, const uint8_t* keep_by_eid,
                    int32_t* out_indptr, int32_t* out_indices, int32_t* out_eid, float* out_vals,
                    void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
 /* CSR -> COO row ids: row[s] = r for indptr[r] <= s < indptr[r+1]. */
-int dg_csr_expand_rows(const int32_t* indptr, int64_t n_rows, int32_t* row, dg_stream_t stream);
+DG_API int dg_csr_expand_rows(const int32_t* indptr, int64_t n_rows, int32_t* row, dg_stream_t stream);
 
 /* ---- SpMM: out[i,:] = epilogue( dst_scale[i] * sum_{s in row i} vals[s] * src_scale[j_s] * x[j_s,:] )
  *      with j_s = indices[s].
@@ -104,13 +111,13 @@ int dg_csr_expand_rows(const int32_t* indptr, int64_t n_rows, int32_t* row, dg_s
  *   flags: DG_SPMM_ACCUMULATE adds into `out`; DG_SPMM_RELU applies max(.,0) last. */
 #define DG_SPMM_ACCUMULATE 1
 #define DG_SPMM_RELU 2
-int dg_spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
+DG_API int dg_spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                     const float* src_scale, const float* dst_scale, const float* bias,
                     const float* x, int64_t ldx, float* out, int64_t ldo,
                     int64_t n_rows, int64_t d, int flags, dg_stream_t stream);
 /* bf16 feature storage, fp32 accumulate, fp32 output (the 2e-2 path). x is __nv_bfloat16 row-major,
  * ldx % 8 == 0 and d % 8 == 0. */
-int dg_spmm_csr_bf16(const int32_t* indptr, const int32_t* indices, const float* vals,
+DG_API int dg_spmm_csr_bf16(const int32_t* indptr, const int32_t* indices, const float* vals,
                      const float* src_scale, const float* dst_scale, const float* bias,
                      const void* x_bf16, int64_t ldx, float* out, int64_t ldo,
                      int64_t n_rows, int64_t d, int flags, dg_stream_t stream);
@@ -124,7 +131,7 @@ int dg_spmm_csr_bf16(const int32_t* indptr, const int32_t* indices, const float*
  * based generator keyed by (seed, pair, unit); p == 0 disables it (eval mode). */
 #define DG_DEC_H1 128
 #define DG_DEC_H2 64
-int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
+DG_API int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
                        const float* pd, const float* ps, const float* w2, const float* b2,
                        const float* w3, const float* b3, float dropout_p, uint64_t seed,
                        float* out, float* z2_save /* nullable: [n_pairs,64] kept for backward */,
@@ -134,8 +141,8 @@ int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
  * dw3 [64], db3 [1] (per-CTA partials summed in CTA order). d pd / d ps are then two deterministic
  * segment sums of dz1 over the decoder graph's CSR / CSC (dg_spmm_csr_f32 with indices = edge ids)
  * -- no atomics. */
-size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs);
-int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
+DG_API size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs);
+DG_API int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
                        const float* pd, const float* ps, const float* w2, const float* w3,
                        float dropout_p, uint64_t seed, const float* z2, const float* dout,
                        float* dz1, float* dw2, float* db2, float* dw3, float* db3,
@@ -145,14 +152,14 @@ int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
 /* Per row of a float64 similarity block [n_rows, n_cols] (leading dimension ld), the k largest
  * entries under the tie rule (value descending, column ascending); out_idx [n_rows,k] ascending.
  * Replaces np.argpartition(-S, k)[:, :k] (data_loader.py:293). k <= 64. */
-int dg_topk_rows_f64(const double* sim, int64_t n_rows, int64_t n_cols, int64_t ld, int k,
+DG_API int dg_topk_rows_f64(const double* sim, int64_t n_rows, int64_t n_cols, int64_t ld, int k,
                      int32_t* out_idx, dg_stream_t stream);
 /* Neighbour lists -> row-normalised symmetric kNN adjacency (A+A^T, +I, D^-1 A in float64, cast to
  * fp32; data_loader.py:294-308 + utils.py:11-17) as a canonical CSR/COO.
  *   nbr [n,k]; outputs sized for the worst case nnz_max = 2*n*k + n: row/col/val [nnz_max],
  *   indptr [n+1]; *nnz_out (device int32) receives the number of distinct entries. */
-size_t dg_knn_graph_workspace_bytes(int64_t n, int k);
-int dg_knn_graph_from_neighbors(const int32_t* nbr, int64_t n, int k, int32_t* indptr,
+DG_API size_t dg_knn_graph_workspace_bytes(int64_t n, int k);
+DG_API int dg_knn_graph_from_neighbors(const int32_t* nbr, int64_t n, int k, int32_t* indptr,
                                 int32_t* row, int32_t* col, float* val, int32_t* nnz_out,
                                 void* workspace, size_t workspace_bytes, dg_stream_t stream);
 

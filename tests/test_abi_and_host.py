@@ -1,0 +1,118 @@
+"""CPU (no GPU needed): the C-ABI library loads and exports every symbol include/dreamgnn.h declares,
+the host-side mirrors keep the reference's parameter names / initialisation, and the product refuses
+to run without CUDA instead of falling back."""
+import argparse
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch as th
+
+import dreamgnn_b200
+from dreamgnn_b200 import _lib, graph as G, layers, ops
+from dreamgnn_b200.model import Net
+from tests import helpers as H
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def built():
+    from dreamgnn_b200 import build
+    return build.build()
+
+
+def test_header_symbols_exported(built):
+    hdr = open(os.path.join(REPO, 'include', 'dreamgnn.h')).read()
+    declared = set(re.findall(r'DG_API[^;(]*?\b(dg_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    out = subprocess.run(['nm', '-D', '--defined-only', built], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r' T (dg_[a-z0-9_]+)', out))
+    assert declared == exported, (declared ^ exported)
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_loads_and_reports_version(built):
+    lib = _lib.load()
+    assert lib.dg_abi_version() == _lib.ABI_VERSION
+    assert lib.dg_scan_workspace_bytes(1000) > 0
+    assert lib.dg_csr_build_workspace_bytes(1000, 10) > lib.dg_csr_build_workspace_bytes(10, 10)
+    assert isinstance(_lib.launch_count(), int)
+
+
+def test_no_cpu_fallback():
+    x = th.randn(4, 8)
+    csr = ops.CSR(th.tensor([0, 1, 2, 3, 4], dtype=th.int32), th.tensor([0, 1, 2, 3], dtype=th.int32),
+                  th.arange(4, dtype=th.int32), None, 4, 4)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.spmm(csr, x)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.decoder_mlp(th.randn(2, 128), th.randn(2, 128), th.randn(64, 128), th.randn(64), th.randn(1, 64),
+                        th.randn(1), None)
+    with pytest.raises(RuntimeError):
+        layers.adjacency_csr(th.eye(3).to_sparse())
+
+
+def _args(g, name):
+    cfg = {'tinyA': dict(layers=3, gcn_agg_units=105, gcn_out_units=16, nhid1=40, nhid2=16),
+           'tinyB': dict(layers=2, gcn_agg_units=96, gcn_out_units=8, nhid1=20, nhid2=8)}[name]
+    return argparse.Namespace(model_activation='leaky', gcn_agg_accum='sum', share_param=True, device='cpu',
+                              dropout=0.0, attention_dropout=0.0, rating_vals=[0, 1],
+                              src_in_units=g['feat.drug'].shape[1], dst_in_units=g['feat.disease'].shape[1],
+                              fdim_drug=g['feat.drug'].shape[0], fdim_disease=g['feat.disease'].shape[0], **cfg)
+
+
+@pytest.mark.parametrize('name', H.CASES)
+def test_net_state_dict_and_init_match_reference(name):
+    """Same keys, shapes AND values as the reference's Net built from the same seed (make_golden.py
+    used th.manual_seed(2024)): construction order and initialisers are mirrored exactly."""
+    g = H.load_golden(name)
+    th.manual_seed(2024)
+    net = Net(_args(g, name))
+    sd = net.state_dict()
+    want = {k[3:]: v for k, v in g.items() if k.startswith('sd.')}
+    assert set(sd) == set(want)
+    for k, v in want.items():
+        np.testing.assert_array_equal(sd[k].numpy(), v, err_msg=k)
+    net.load_state_dict({k: th.tensor(v) for k, v in want.items()})   # checkpoints interchange
+
+
+def test_graph_handle_structure_on_cpu():
+    g = H.load_golden('tinyA')
+    data = {}
+    for et in ('0', '1'):
+        s, d = g[f'train.enc.{et}']
+        data[('drug', et, 'disease')] = (s, d)
+        data[('disease', 'rev-' + et, 'drug')] = (d, s)
+    hg = G.heterograph(data, num_nodes_dict={'drug': 60, 'disease': 45})
+    assert hg.canonical_etypes == [('disease', 'rev-0', 'drug'), ('disease', 'rev-1', 'drug'),
+                                   ('drug', '0', 'disease'), ('drug', '1', 'disease')]
+    assert hg.etypes == ['rev-0', 'rev-1', '0', '1'] and hg.ntypes == ['disease', 'drug']
+    assert hg.number_of_edges('0') == g['train.enc.0'].shape[1]
+    rel = hg['0']
+    assert rel.number_of_src_nodes() == 60 and rel.number_of_dst_nodes() == 45
+    np.testing.assert_array_equal(rel.in_degrees().numpy(), np.bincount(g['train.enc.0'][1], minlength=45))
+    hg.nodes['drug'].data['ci'] = th.ones(60, 1)
+    assert rel.srcdata['ci'] is hg.nodes['drug'].data['ci']           # slices share node data
+    with rel.local_scope():
+        rel.srcdata['h'] = th.zeros(60, 3)
+    assert 'h' not in hg.nodes['drug'].data
+    i32 = hg.int()
+    assert i32.idtype == th.int32 and hg.int() is i32                  # conversions are cached
+    with pytest.raises(RuntimeError, match='CUDA'):
+        hg.block('drug')
+    c = hg.clone()
+    c.add_edges([0], [0], etype='0')
+    assert c.number_of_edges('0') == hg.number_of_edges('0') + 1
+
+
+def test_package_has_no_oracle_dependency():
+    pkg = os.path.dirname(dreamgnn_b200.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(root, f)).read()
+                assert 'oracle' not in src.replace('oracle/', '').lower() or f == 'none', f
+                assert 'import dgl' not in src, f

@@ -1,0 +1,308 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the CPU oracle (oracle/restate.py,
+numpy, scipy) on the same seeded inputs. Bit-exact for integer / index work and for the fp32
+normaliser / adjacency values; norm-wise <= 1e-5 for fp32 arithmetic, <= 2e-2 for bf16 storage."""
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import restate as R
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5      # north_star: within 1e-5 relative for fp32 forward and backward
+BF16_TOL = 2e-2      # north_star: within 2e-2 for the bf16 path
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from dreamgnn_b200 import _lib
+    _lib.load()                      # fail loudly if the extension is missing
+    return th.device('cuda:0')
+
+
+def ops():
+    from dreamgnn_b200 import ops as _ops
+    return _ops
+
+
+# ---- index primitives -----------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [0, 1, 5, 4096, 4097, 100003, 1 << 21])
+def test_exclusive_scan(dev, n):
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 50, size=n).astype(np.int32)
+    got = ops().exclusive_scan_i32(th.tensor(x, device=dev)).cpu().numpy()
+    want = np.concatenate([[0], np.cumsum(x, dtype=np.int64)]).astype(np.int32)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize('n,bits', [(1, 8), (2049, 13), (50000, 35), (300001, 47)])
+def test_radix_sort_is_stable(dev, n, bits):
+    rng = np.random.default_rng(bits)
+    keys = rng.integers(0, 1 << min(bits, 12), size=n, dtype=np.int64) << max(bits - 12, 0)   # many duplicates
+    keys |= rng.integers(0, 4, size=n, dtype=np.int64)
+    vals = np.arange(n, dtype=np.int32)
+    ko, vo = ops().sort_pairs_u64(th.tensor(keys, device=dev), th.tensor(vals, device=dev), bits)
+    order = np.argsort(keys, kind='stable')
+    np.testing.assert_array_equal(ko.cpu().numpy(), keys[order])
+    np.testing.assert_array_equal(vo.cpu().numpy(), vals[order])
+
+
+# ---- CSR build / transpose / normalisers ----------------------------------------------------------
+@pytest.mark.parametrize('n_rows,n_cols,n_edges', [(7, 5, 0), (1, 1, 1), (45, 120, 2430), (1000, 777, 60000),
+                                                  (3, 100000, 5000)])
+def test_csr_build_matches_oracle(dev, n_rows, n_cols, n_edges):
+    rng = np.random.default_rng(n_edges + 1)
+    row = rng.integers(0, n_rows, size=n_edges)
+    col = rng.integers(0, n_cols, size=n_edges)                # duplicates and empty rows on purpose
+    csr = ops().CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), n_rows, n_cols)
+    indptr, indices, eid = R.csr_from_pairs(row, col, n_rows)
+    np.testing.assert_array_equal(csr.indptr.cpu().numpy(), indptr)
+    np.testing.assert_array_equal(csr.indices.cpu().numpy(), indices)
+    np.testing.assert_array_equal(csr.eid.cpu().numpy(), eid)
+    t = csr.transpose()
+    tp, ti, te = R.csr_from_pairs(col, row, n_cols)
+    np.testing.assert_array_equal(t.indptr.cpu().numpy(), tp)
+    np.testing.assert_array_equal(t.indices.cpu().numpy(), ti)
+    np.testing.assert_array_equal(t.eid.cpu().numpy(), te)
+    np.testing.assert_array_equal(csr.degree_norm().cpu().numpy(), R.degree_norm(np.diff(indptr)))   # bit-exact
+    if n_edges:
+        np.testing.assert_array_equal(csr.rows().cpu().numpy(), row[eid])
+
+
+def test_csr_matches_scipy_on_distinct_pairs(dev):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    cells = rng.choice(300 * 200, size=9000, replace=False)
+    row, col = cells // 200, cells % 200
+    csr = ops().CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), 300, 200)
+    m = sp.csr_matrix((np.ones(9000), (row, col)), shape=(300, 200))
+    m.sort_indices()
+    np.testing.assert_array_equal(csr.indptr.cpu().numpy(), m.indptr)
+    np.testing.assert_array_equal(csr.indices.cpu().numpy(), m.indices)
+
+
+def test_degree_norm_exhaustive_small_degrees(dev):
+    from dreamgnn_b200 import graph_build
+    deg = th.arange(0, 70000, device=dev)
+    got = graph_build._norm_from_degrees(deg).cpu().numpy()
+    np.testing.assert_array_equal(got, R.degree_norm(np.arange(70000)))
+
+
+# ---- edge dropout as CSR compaction ----------------------------------------------------------------
+@pytest.mark.parametrize('rate', [0.1, 0.5, 0.999])
+def test_edge_dropout_compaction(dev, rate):
+    rng = np.random.default_rng(11)
+    n_rows, n_cols, e = 83, 61, 4000
+    row, col = rng.integers(0, n_rows, e), rng.integers(0, n_cols, e)
+    val = rng.random(e).astype(np.float32)
+    o = ops()
+    base = o.CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), n_rows, n_cols,
+                          th.tensor(val, device=dev))
+    perm = th.randperm(e, generator=th.Generator().manual_seed(5))
+    keep = R.edge_dropout_keep(perm.numpy(), rate)
+    flags = o.keep_flags(e, [(perm.to(dev), len(keep), 0)], dev)
+    got = o.csr_dropout(base, flags, len(keep))
+    for g, (r_, c_) in ((got, (row, col)), (got.transpose(), (col, row))):
+        indptr, indices, eid = R.csr_from_pairs(r_[keep], c_[keep], g.n_rows)
+        np.testing.assert_array_equal(g.indptr.cpu().numpy(), indptr)
+        np.testing.assert_array_equal(g.indices.cpu().numpy(), indices)
+        np.testing.assert_array_equal(g.eid.cpu().numpy(), keep[eid])          # ids still name base edges
+        np.testing.assert_array_equal(g.vals.cpu().numpy(), val[keep][eid])
+
+
+# ---- SpMM ------------------------------------------------------------------------------------------
+def _dense_spmm(row, col, val, n_rows, x, ss, ds, bias, relu):
+    x64 = x.double() * (ss.double()[:, None] if ss is not None else 1.0)
+    out = th.zeros(n_rows, x.shape[1], dtype=th.float64)
+    w = th.tensor(val, dtype=th.float64)[:, None] if val is not None else 1.0
+    out.index_add_(0, th.tensor(row), x64[th.tensor(col)] * w)
+    if ds is not None:
+        out = out * ds.double()[:, None]
+    if bias is not None:
+        out = out + bias.double()
+    return out.relu() if relu else out
+
+
+@pytest.mark.parametrize('d', [4, 36, 128, 256, 344, 512, 768])
+@pytest.mark.parametrize('weighted,scaled,epi', [(False, False, False), (False, True, False), (True, False, True),
+                                                  (True, True, True)])
+def test_spmm_forward_backward(dev, d, weighted, scaled, epi):
+    rng = np.random.default_rng(d)
+    n_rows, n_cols, e = 70, 90, 2500
+    row, col = rng.integers(0, n_rows, e), rng.integers(0, n_cols, e)
+    row[row == 3] = 4                                            # an empty row
+    val = rng.random(e).astype(np.float32) if weighted else None
+    g = th.Generator().manual_seed(d)
+    x = th.randn(n_cols, d, generator=g)
+    ss = th.rand(n_cols, generator=g) if scaled else None
+    ds = th.rand(n_rows, generator=g) if scaled else None
+    bias = th.randn(d, generator=g) if epi else None
+    o = ops()
+    csr = o.CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), n_rows, n_cols,
+                         th.tensor(val, device=dev) if weighted else None)
+    xg = x.to(dev).requires_grad_(True)
+    bg = bias.to(dev).requires_grad_(True) if epi else None
+    out = o.spmm(csr, xg, ss.to(dev) if scaled else None, ds.to(dev) if scaled else None, bg, relu=epi)
+    want = _dense_spmm(row, col, val, n_rows, x, ss, ds, bias, epi)
+    assert H.rel_err(out.detach().cpu(), want) <= FP32_TOL
+    gout = th.randn(n_rows, d, generator=g)
+    out.backward(gout.to(dev))
+    xr = x.clone().double().requires_grad_(True)
+    br = bias.clone().double().requires_grad_(True) if epi else None
+    ref = _dense_spmm(row, col, val, n_rows, xr, ss, ds, br, epi)
+    ref.backward(gout.double())
+    assert H.rel_err(xg.grad.cpu(), xr.grad) <= FP32_TOL
+    if epi:
+        assert H.rel_err(bg.grad.cpu(), br.grad) <= FP32_TOL
+    # atomic-free claim: a second run is bit-identical
+    out2 = o.spmm(csr, xg.detach(), ss.to(dev) if scaled else None, ds.to(dev) if scaled else None,
+                  bg.detach() if epi else None, relu=epi)
+    assert th.equal(out2, out.detach())
+
+
+@pytest.mark.parametrize('d', [8, 128, 344, 768])
+def test_spmm_bf16_storage(dev, d):
+    rng = np.random.default_rng(d)
+    n_rows, n_cols, e = 64, 80, 3000
+    row, col = rng.integers(0, n_rows, e), rng.integers(0, n_cols, e)
+    x = th.randn(n_cols, d, generator=th.Generator().manual_seed(1))
+    ss = th.rand(n_cols, generator=th.Generator().manual_seed(2))
+    o = ops()
+    csr = o.CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), n_rows, n_cols)
+    out = o.spmm(csr, x.to(dev).to(th.bfloat16), ss.to(dev), None)
+    assert out.dtype == th.float32
+    assert H.rel_err(out.cpu(), _dense_spmm(row, col, None, n_rows, x, ss, None, None, False)) <= BF16_TOL
+    exact = _dense_spmm(row, col, None, n_rows, x.to(th.bfloat16).float(), ss, None, None, False)
+    assert H.rel_err(out.cpu(), exact) <= FP32_TOL               # only the storage rounding differs
+
+
+def test_spmm_rejects_bad_layout(dev):
+    o = ops()
+    csr = o.CSR.from_coo(th.tensor([0], device=dev), th.tensor([0], device=dev), 1, 1)
+    with pytest.raises(RuntimeError, match='multiples'):
+        o.spmm(csr, th.randn(1, 5, device=dev))
+
+
+# ---- decoder ---------------------------------------------------------------------------------------
+def _decoder_params(gen, n_in):
+    P = {'decoder.lin1.weight': th.randn(128, 2 * n_in, generator=gen) * 0.2,
+         'decoder.lin1.bias': th.randn(128, generator=gen) * 0.1,
+         'decoder.lin2.weight': th.randn(64, 128, generator=gen) * 0.2,
+         'decoder.lin2.bias': th.randn(64, generator=gen) * 0.1,
+         'decoder.lin3.weight': th.randn(1, 64, generator=gen) * 0.2,
+         'decoder.lin3.bias': th.randn(1, generator=gen) * 0.1}
+    return P
+
+
+@pytest.mark.parametrize('n_pairs', [0, 1, 63, 128, 1000, 40000])
+def test_decoder_forward_backward(dev, n_pairs):
+    from dreamgnn_b200.layers import MLPDecoder
+    from dreamgnn_b200 import graph as G
+    gen = th.Generator().manual_seed(n_pairs)
+    n_d, n_s, n_in = 37, 29, 16
+    rng = np.random.default_rng(n_pairs)
+    src, dst = rng.integers(0, n_d, n_pairs), rng.integers(0, n_s, n_pairs)
+    hd, hs = th.randn(n_d, n_in, generator=gen), th.randn(n_s, n_in, generator=gen)
+    P = _decoder_params(gen, n_in)
+    dec = MLPDecoder(n_in, dropout_rate=0.3)
+    dec.load_state_dict({k[len('decoder.'):]: v for k, v in P.items()})
+    dec = dec.to(dev).eval()
+    g = G.heterograph({('drug', 'rate', 'disease'): (src, dst)}, {'drug': n_d, 'disease': n_s}).int().to(dev)
+    hdg, hsg = hd.to(dev).requires_grad_(True), hs.to(dev).requires_grad_(True)
+    out = dec(g, hdg, hsg)
+    assert out.shape == (n_pairs, 1)
+    Pr = {k: v.clone().double().requires_grad_(True) for k, v in P.items()}
+    hdr, hsr = hd.double().requires_grad_(True), hs.double().requires_grad_(True)
+    ref = R.mlp_decoder(Pr, 'decoder.', src, dst, hdr, hsr)
+    assert H.rel_err(out.detach().cpu(), ref.detach()) <= FP32_TOL
+    if n_pairs == 0:
+        return
+    gout = th.randn(n_pairs, 1, generator=gen)
+    out.backward(gout.to(dev))
+    ref.backward(gout.double())
+    assert H.rel_err(hdg.grad.cpu(), hdr.grad) <= FP32_TOL
+    assert H.rel_err(hsg.grad.cpu(), hsr.grad) <= FP32_TOL
+    for k, p in dec.named_parameters():
+        assert H.rel_err(p.grad.cpu(), Pr['decoder.' + k].grad) <= FP32_TOL, k
+    # deterministic (atomic-free) backward
+    g1 = hdg.grad.clone()
+    hdg.grad = None
+    dec.zero_grad()
+    dec(g, hdg, hsg).backward(gout.to(dev))
+    assert th.equal(hdg.grad, g1)
+
+
+def test_decoder_dropout_is_consistent_between_forward_and_backward(dev):
+    """Training mode: the backward regenerates the forward's masks. Checked as a directional derivative of
+    the (piecewise-linear, fixed-seed) function, plus the keep rate and the 1/(1-p) scaling."""
+    o = ops()
+    gen = th.Generator().manual_seed(7)
+    n_d, n_s, e, p = 50, 40, 6000, 0.3
+    rng = np.random.default_rng(7)
+    pairs = o.PairGraph(th.tensor(rng.integers(0, n_d, e), device=dev), th.tensor(rng.integers(0, n_s, e), device=dev),
+                        n_d, n_s)
+    mk = lambda *s: (th.randn(*s, generator=gen) * 0.3).to(dev)
+    pd, ps, w2, b2, w3, b3 = mk(n_d, 128), mk(n_s, 128), mk(64, 128), mk(64), mk(1, 64), mk(1)
+
+    def f(pd_, w2_):
+        return o.decoder_mlp(pd_, ps, w2_, b2, w3, b3, pairs, p=p, seed=1234, training=True)
+    pd_g, w2_g = pd.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+    out = f(pd_g, w2_g)
+    assert th.equal(out.detach(), f(pd, w2))                      # same seed -> same masks
+    assert not th.equal(out.detach(), o.decoder_mlp(pd, ps, w2, b2, w3, b3, pairs, p=p, seed=99, training=True))
+    gout = th.randn(e, 1, generator=gen).to(dev)
+    out.backward(gout)
+    dpd, dw2 = mk(n_d, 128), mk(64, 128)
+    eps = 1e-3
+    fd = ((f(pd + eps * dpd, w2 + eps * dw2).double() - f(pd - eps * dpd, w2 - eps * dw2).double()) * gout).sum() / (2 * eps)
+    an = (pd_g.grad.double() * dpd).sum() + (w2_g.grad.double() * dw2).sum()
+    assert abs(float(fd - an)) <= 2e-2 * abs(float(an)) + 1e-3
+    # keep-rate of the first dropout: eval/(train) ratio on a linear probe
+    z2 = th.empty(e, 64, device=dev)
+    lib = o.L.load()
+    outp = th.empty(e, device=dev)
+    big = th.full((n_d, 128), 5.0, device=dev)
+    o.L.check(lib.dg_decoder_fwd_f32(o.L.ptr(pairs.src), o.L.ptr(pairs.dst), e, o.L.ptr(big), o.L.ptr(th.zeros_like(ps)),
+                                     o.L.ptr(th.ones(64, 128, device=dev)), o.L.ptr(th.zeros(64, device=dev)),
+                                     o.L.ptr(th.ones(64, device=dev)), o.L.ptr(th.zeros(1, device=dev)), p, 42,
+                                     o.L.ptr(outp), o.L.ptr(z2), o.L.stream()), 'decoder_fwd')
+    kept2 = float((z2 > 0).float().mean())
+    assert abs(kept2 - (1 - p)) < 0.01
+    # every z2 entry = (number of kept z1 units) * 5/(1-p) /(1-p) when kept: mean over kept ~ 128*5/(1-p)
+    mean_kept = float(z2[z2 > 0].mean())
+    assert abs(mean_kept - 128 * 5.0 / (1 - p)) / (128 * 5.0 / (1 - p)) < 0.01
+
+
+# ---- kNN --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,k', [(8, 3), (60, 4), (333, 15), (1000, 33), (200, 64)])
+def test_topk_rows(dev, n, k):
+    rng = np.random.default_rng(n)
+    sim = rng.random((n, n + 7))
+    sim[:, 5] = sim[:, 2]                                         # exact ties -> (value desc, index asc)
+    got = ops().topk_rows(th.tensor(sim, device=dev), k).cpu().numpy()
+    order = np.lexsort((np.broadcast_to(np.arange(n + 7), sim.shape), -sim), axis=1)[:, :k]
+    np.testing.assert_array_equal(got, np.sort(order, axis=1))
+
+
+@pytest.mark.parametrize('n,k', [(5, 2), (60, 4), (500, 15), (3000, 40)])
+def test_knn_graph_from_neighbors_bit_exact(dev, n, k):
+    rng = np.random.default_rng(n + k)
+    nbr = np.stack([rng.choice(n, size=k, replace=False) for _ in range(n)])
+    for i in range(n // 2):                                       # self among the neighbours for half the rows
+        if i not in nbr[i]:
+            nbr[i, 0] = i
+    nbr = np.sort(nbr, axis=1)
+    csr, rows = ops().knn_graph_from_neighbors(th.tensor(nbr, device=dev))
+    row, col, val = R.knn_graph_from_neighbors(nbr, n)
+    np.testing.assert_array_equal(rows.cpu().numpy(), row)
+    np.testing.assert_array_equal(csr.indices.cpu().numpy(), col)
+    np.testing.assert_array_equal(csr.vals.cpu().numpy(), val)     # bit-exact fp32
+    np.testing.assert_array_equal(csr.indptr.cpu().numpy(), np.concatenate([[0], np.cumsum(np.bincount(row, minlength=n))]))
+
+
+def test_launch_counter_counts_kernels(dev):
+    from dreamgnn_b200 import _lib
+    _lib.reset_launch_count()
+    ops().exclusive_scan_i32(th.ones(10000, dtype=th.int32, device=dev))
+    assert _lib.launch_count() == 3
