@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of DREAM-GNN's message-passing hot path on B200 (driver contract: one JSON line).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload syn20m|lrssl|gdataset|cdataset]
+    python bench.py --impl reference ...        # the reference's algorithm on the host CPU cores
+
+A "step" is one full training iteration (train.py:250-300): per-iteration augmentation (edge dropout
++ feature noise with the CSR rebuild), Net.forward, BCE + common loss, backward, clip, Adam.
+metric = aggregated edges per second: sum of nnz over every GCMC and FGCN SpMM launch (forward and
+backward) of one iteration / iteration time. iters/s is reported beside it.
+
+N > 1: one process per GPU (torchrun), each rank trains its own fold-replica of the same shape with
+no data-path collective (cross-validation folds shard embarrassingly) -> weak scaling; the timed
+region is bracketed by barrier + synchronize and the reported time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch as th
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+HBM_FALLBACK_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------
+def measured_peak():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return HBM_FALLBACK_GBS, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def spmm_algorithmic_bytes(nnz, n_rows, n_cols, d, elem, valued):
+    """SURVEY.md 8d gather model, the per-unit figure of the roofline: every stored edge reads its column
+    index (+ value) and one d-wide source row; every output row is written once; indptr and the two
+    scale vectors are read once."""
+    return nnz * (4 + (4 if valued else 0) + d * elem) + n_rows * d * 4 + (n_rows + 1) * 4 + (n_rows + n_cols) * 4
+
+
+def spmm_compulsory_bytes(nnz, n_rows, n_cols, d, elem, valued):
+    """B_min of SURVEY.md 8d: every operand touched exactly once (perfect reuse of gathered rows)."""
+    return nnz * (4 + (4 if valued else 0)) + (n_rows + 1) * 4 + n_cols * d * elem + n_rows * d * 4 + (n_rows + n_cols) * 4
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    from dreamgnn_b200 import _lib, ops, synthetic
+    from dreamgnn_b200.model import Net
+    from dreamgnn_b200.train import train_iteration, aug_params_from_args
+    from dreamgnn_b200.utils import common_loss, common_loss_gram
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not th.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
+    th.cuda.set_device(local)
+    dev = th.device('cuda', local)
+    _lib.load()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    spec = synthetic.scaled(args.workload, args.scale)
+    th.manual_seed(1234 + rank)
+    w = synthetic.make_workload(spec, dev, seed=1234 + rank)            # each rank: its own fold-replica
+    state = synthetic.train_state(w, dev)
+    margs = synthetic.model_args(w)
+    model = Net(margs).to(dev)
+    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5)
+    loss_fn = th.nn.BCEWithLogitsLoss()
+    aug_methods = ['edge_dropout', 'feature_noise']
+    aug_params = aug_params_from_args(argparse.Namespace())
+    closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
+    step = lambda: train_iteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-timed, SpMM launches logged with events -------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.PROFILE = []
+    _lib.reset_launch_count()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count()
+    log, ops.PROFILE = ops.PROFILE, None
+    clocks = sampler.stop()
+    t = th.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- e2e: same K steps through the public API, host buffers in / loss out every step -----------
+    host = {k: getattr(state, k).cpu().pin_memory() for k in ('drug_feat', 'dis_feat', 'labels')}
+    sim_is_feat = state.drug_sim_feat is state.drug_feat
+    if not sim_is_feat:
+        host['drug_sim_feat'] = state.drug_sim_feat.cpu().pin_memory()
+        host['dis_sim_feat'] = state.dis_sim_feat.cpu().pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        for k, v in host.items():
+            setattr(state, k, v.to(dev, non_blocking=True))
+        if sim_is_feat:
+            state.drug_sim_feat, state.dis_sim_feat = state.drug_feat, state.dis_feat
+        loss_host = float(step().item())                                  # D2H read of the step's result
+    e1.record()
+    barrier()
+    t = th.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+
+    # ---- metric ---------------------------------------------------------------------------------
+    agg_edges = sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / args.steps
+    it_s = args.steps / (ms_max / 1e3)
+    value = world * agg_edges * it_s / 1e9
+    e2e_value = world * agg_edges * (args.steps / (ms_e2e / 1e3)) / 1e9
+
+    # ---- roofline of the dominant kernel (largest total device time among the logged SpMM classes) --
+    classes = {}
+    for tag, nnz, nr, nc, d, el, valued, a, b in log:
+        key = (tag.split('.')[0], d, el)
+        c = classes.setdefault(key, dict(ms=0.0, bytes=0.0, bmin=0.0, n=0, nnz=0))
+        c['ms'] += a.elapsed_time(b)
+        c['bytes'] += spmm_algorithmic_bytes(nnz, nr, nc, d, el, valued)
+        c['bmin'] += spmm_compulsory_bytes(nnz, nr, nc, d, el, valued)
+        c['n'] += 1
+        c['nnz'] += nnz
+    top_key, top = max(classes.items(), key=lambda kv: kv[1]['ms'])
+    peak, peak_src = measured_peak()
+    achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
+    if os.path.isfile(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh).get('%s_d%d' % (top_key[0], top_key[1]))
+    roofline = {'bound': 'hbm', 'kernel': 'spmm_csr_kernel (%s, d=%d, %d-byte features)' % top_key,
+                'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
+                'traffic': traffic, 'peak_source': peak_src, 'launches_timed': top['n'],
+                'avg_launch_ms': round(top['ms'] / top['n'], 4),
+                'algorithmic_bytes_per_launch': int(top['bytes'] / top['n']),
+                'model': 'gather: nnz*(4[+4]+d*s) + n_rows*d*4 + index/scale vectors (SURVEY 8d)',
+                'compulsory_frac': round(top['bmin'] / (top['ms'] / 1e3) / 1e9 / peak, 4),
+                'share_of_step': round(top['ms'] / ms, 4),
+                'all_spmm_classes': {'%s_d%d_b%d' % k: {'ms_per_step': round(v['ms'] / args.steps, 3),
+                                                        'GBps': round(v['bytes'] / (v['ms'] / 1e3) / 1e9, 1),
+                                                        'GEps': round(v['nnz'] / (v['ms'] / 1e3) / 1e9, 2)}
+                                     for k, v in classes.items()}}
+
+    out = {'metric': 'aggregated_edges_per_sec', 'value': round(value, 4), 'unit': 'GE/s', 'n_gpus': world,
+           'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_max / args.steps, 3),
+           'iters_per_sec': round(world * it_s, 4), 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': '%s: %d drugs x %d diseases, %d scored pairs, %d-/%d-dim features, k=%d, '
+                                  'GCMC+FGCN 3 layers, 128 units, one fold per GPU'
+                                  % (args.workload, spec['n_drug'], spec['n_dis'], state.labels.numel(),
+                                     spec['f_drug'], spec['f_dis'], spec['k']),
+                      'step': 'augmentation + forward + loss + backward + clip + Adam (train.py:250-300)',
+                      'aggregated_edges_per_step': int(agg_edges), 'scale': args.scale,
+                      'l2': 'inputs larger than L2 (gathered operand %.0f MB, indices %.0f MB per SpMM)'
+                            % (top['bmin'] / top['n'] / 1e6, top['nnz'] / top['n'] * 4 / 1e6)
+                            if top['bmin'] / top['n'] > 126e6 else 'working set fits L2; no flush between steps',
+                      'parallelism': 'fold-replica per GPU, no collective' if world > 1 else 'single GPU',
+                      'common_loss': 'N x N (reference form)' if spec['kind'] == 'dense' else
+                                     'Gram-matrix form of the same value (N x N does not fit at this shape)',
+                      'fgcn_input': 'N x N similarity (reference)' if spec['kind'] == 'dense' else
+                                    'feature matrix (N x N similarity infeasible at this shape)'},
+           'e2e': {'value': round(e2e_value, 4), 'unit': 'GE/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
+                   'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
+                   'what': 'features + labels copied from pinned host memory every step, loss read back; graph '
+                           'structure stays resident as in the reference training loop (train.py:186-200)'},
+           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
+           'final_loss': round(loss_host, 6)}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_reference(args, steps=1, warmup=1)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle/restate.py port -- the reference is pure Python + DGL and
+# cannot travel to the GPU box) on all host cores, on a bounded proportional sample of the workload
+# ---------------------------------------------------------------------------------------------------
+def cpu_sample_workload(workload, scale, seed=1234):
+    """Same generator as the GPU arm, on CPU with numpy/torch: a proportional replica (nodes and pairs
+    scaled together, widths and k unchanged) so the per-edge work matches the full shape."""
+    import numpy as np
+    from dreamgnn_b200 import synthetic
+    from oracle import restate as R
+    spec = synthetic.scaled(workload, scale)
+    gen = th.Generator().manual_seed(seed)
+    n_d, n_s = spec['n_drug'], spec['n_dis']
+    if spec['kind'] == 'sparse':
+        cells = th.unique(th.randint(0, n_d * n_s, (spec['n_pairs'],), generator=gen))
+        labels = (th.rand(cells.numel(), generator=gen) < 0.01).float()
+        fdim = (spec['f_drug'], spec['f_dis'])
+    else:
+        perm = th.randperm(n_d * n_s, generator=gen)
+        pos, neg = perm[:spec['n_pos']], perm[spec['n_pos']:]
+        pos, neg = pos[:int(pos.numel() * 0.9)], neg[:int(neg.numel() * 0.9)]
+        cells = th.cat([th.sort(pos).values, th.sort(neg).values])
+        labels = th.cat([th.ones(pos.numel()), th.zeros(neg.numel())])
+        fdim = (n_d, n_s)
+    order = th.argsort(labels, descending=True, stable=True)
+    cells, labels = cells[order], labels[order]
+    pairs = ((cells // n_s).numpy(), (cells % n_s).numpy())
+    drug_feat = th.nn.functional.normalize(th.randn(n_d, spec['f_drug'], generator=gen), dim=1)
+    dis_feat = th.nn.functional.normalize(th.randn(n_s, spec['f_dis'], generator=gen), dim=1)
+    enc = R.enc_graph_from_pairs(pairs, labels.numpy(), n_d, n_s)
+
+    def knn(x):
+        x = np.asarray(x, dtype=np.float64)
+        row, col, val = R.similarity_knn_graph(R.feature_cosine_similarity(x), spec['k'])
+        return row, col, val, x.shape[0]
+    emb_d = th.randn(n_d, 64, generator=gen).numpy()
+    emb_s = th.randn(n_s, 64, generator=gen).numpy()
+    graphs = [knn(emb_d), knn(emb_s), knn(drug_feat.numpy()), knn(dis_feat.numpy())]
+    if spec['kind'] == 'sparse':
+        sims = (drug_feat, dis_feat)
+    else:
+        sims = (th.tensor(R.feature_cosine_similarity(emb_d), dtype=th.float32),
+                th.tensor(R.feature_cosine_similarity(emb_s), dtype=th.float32))
+    return spec, enc, pairs, labels, graphs, (drug_feat, dis_feat, sims[0], sims[1]), fdim
+
+
+def cpu_reference(args, steps, warmup, budget_s=25.0, scale=None):
+    """Time `steps` full training iterations of the oracle port on all host cores. Unless --cpu-scale is
+    given the sample size is calibrated from a small probe so that (warmup + steps) fit `budget_s`."""
+    from dreamgnn_b200 import synthetic
+    from dreamgnn_b200.model import Net
+    from oracle import restate as R
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    if scale is None:
+        scale = args.cpu_scale
+    if not scale:
+        sparse = args.workload.startswith('syn')
+        cap = args.scale / 40.0 if sparse else args.scale
+        probe_scale = min(cap, 0.004 if sparse else 0.25)
+        probe = cpu_reference(args, steps=1, warmup=0, scale=probe_scale)
+        per_pair = probe['ms_per_step'] / 1e3 / probe['pairs']
+        want_pairs = budget_s / max(steps + warmup, 1) / per_pair
+        full_pairs = probe['pairs'] / (probe_scale if sparse else probe_scale ** 2)
+        scale = min(cap, want_pairs / full_pairs if sparse else (want_pairs / full_pairs) ** 0.5)
+        scale = max(scale, probe_scale)
+    spec, enc, pairs, labels, graphs, feats, fdim = cpu_sample_workload(args.workload, scale)
+    w = dict(drug_feat=feats[0], dis_feat=feats[1], fdim_drug=fdim[0], fdim_disease=fdim[1])
+    th.manual_seed(1234)
+    sd = Net(synthetic.model_args(w, device='cpu')).state_dict()        # random init of the same architecture
+    P = {k: v.clone() for k, v in sd.items()}
+    for k in list(P):
+        if '.ifc.' in k:
+            P[k] = P[k.replace('.ifc.', '.ufc.')]
+    leaves = list({id(v): v for v in P.values()}.values())
+    for v in leaves:
+        v.requires_grad_(True)
+    opt = th.optim.Adam(leaves, lr=0.002, weight_decay=1e-5)
+    cfg = dict(layers=3, dropout=0.3, attention_dropout=0.1)
+    kept = sum(R.dropout_num_keep(len(s), 0.1) for s, _ in enc['edges'].values())
+    knn_kept = sum(R.dropout_num_keep(len(g[2]), 0.1) for g in graphs)
+    agg_edges = 3 * 2 * kept + 4 * knn_kept        # GCMC: 3 layers x (fwd+bwd) x all 4 etypes; FGCN: 2 layers x (fwd+bwd)
+    for _ in range(warmup):
+        R.train_iteration(P, opt, 0, enc, pairs, labels, graphs, feats, cfg)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.train_iteration(P, opt, 0, enc, pairs, labels, graphs, feats, cfg)
+    dt = (time.perf_counter() - t0) / steps
+    cpu_model = ''
+    try:
+        with open('/proc/cpuinfo') as fh:
+            cpu_model = next((ln.split(':', 1)[1].strip() for ln in fh if ln.startswith('model name')), '')
+    except OSError:
+        pass
+    return {'value': round(agg_edges / dt / 1e9, 6), 'unit': 'GE/s', 'cores': cores, 'kind': 'port',
+            'sample': '%s at scale %.4g: %d drugs x %d diseases, %d scored pairs, same widths/k; %d step(s) of the '
+                      'full training iteration (oracle/restate.py = reference algorithm on a DGL stand-in), '
+                      '%.2f s/step, torch threads=%d, cpu="%s"'
+                      % (args.workload, scale, spec['n_drug'], spec['n_dis'], len(labels), steps, dt,
+                         th.get_num_threads(), cpu_model),
+            'ms_per_step': round(dt * 1e3, 1), 'iters_per_sec_sample': round(1.0 / dt, 4), 'pairs': len(labels),
+            'aggregated_edges_per_step_sample': int(agg_edges)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if rank != 0:
+        return                                       # rank 0 alone runs the CPU arm; others exit 0
+    base = cpu_reference(args, steps=args.steps, warmup=args.warmup, budget_s=150.0)
+    from dreamgnn_b200 import synthetic
+    spec = synthetic.scaled(args.workload, args.scale)
+    out = {'impl': 'reference', 'metric': 'aggregated_edges_per_sec', 'value': base['value'], 'unit': 'GE/s',
+           'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': base['ms_per_step'],
+           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': '%s (%d drugs x %d diseases) -- timed on the bounded sample named in cpu_baseline'
+                                  % (args.workload, spec['n_drug'], spec['n_dis']),
+                      'step': 'augmentation + forward + loss + backward + clip + Adam (train.py:250-300)'},
+           'cpu_baseline': base,
+           'e2e': {'value': base['value'], 'unit': 'GE/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+           'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='syn20m', choices=['syn20m', 'lrssl', 'gdataset', 'cdataset'])
+    ap.add_argument('--scale', type=float, default=1.0, help='proportional shrink of the workload (tests)')
+    ap.add_argument('--cpu-scale', type=float, default=0.0, help='scale of the CPU sample (default: scale/40 for syn*)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -113,7 +113,7 @@ class GCMCGraphConv(nn.Module):
                 feat = dot_or_identity(feat, weight, self.device)
             d = feat.shape[1]
             rst = ops.spmm(graph.etype_csr(), _pad_cols(feat, 4), src_scale=_flat_f32(self.dropout(cj)),
-                           dst_scale=_flat_f32(ci))
+                           dst_scale=_flat_f32(ci), tag='gcmc')
         return rst[:, :d]
 
 
@@ -209,7 +209,7 @@ class GCMCLayer(nn.Module):
             if MESSAGE_DTYPE != th.float32:
                 h = h.to(MESSAGE_DTYPE)
             agg = ops.spmm(blk.csr, h.view(blk.n_src * blk.num_rel, dp), src_scale=scale,
-                           dst_scale=_flat_f32(graph.nodes[dst_type].data['ci']))
+                           dst_scale=_flat_f32(graph.nodes[dst_type].data['ci']), tag='gcmc')
             out[dst_type] = agg[:, :D] if dp != D else agg
         drug = self.dropout(self.agg_act(out['drug']))
         dis = self.dropout(self.agg_act(out['disease']))
@@ -244,7 +244,7 @@ class GraphConvolution(nn.Module):
         if d % 4:
             support = _pad_cols(support, 4)
             bias = _pad_cols(bias, 4) if bias is not None else None
-        out = ops.spmm(adjacency_csr(adj), support, bias=bias, relu=relu)
+        out = ops.spmm(adjacency_csr(adj), support, bias=bias, relu=relu, tag='fgcn')
         return out[:, :d] if out.shape[1] != d else out
 
     def forward(self, input, adj):

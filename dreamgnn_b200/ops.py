@@ -166,7 +166,12 @@ def csr_dropout(csr, flags, n_keep):
 # ------------------------------------------------------------------------------------------------
 # SpMM
 # ------------------------------------------------------------------------------------------------
-def _spmm_raw(csr, x, src_scale=None, dst_scale=None, bias=None, flags=0, out=None):
+# Optional launch log for bench.py's roofline: when PROFILE is a list every SpMM launch appends
+# (tag, nnz, n_rows, n_cols, d, element bytes, valued, start event, end event).
+PROFILE = None
+
+
+def _spmm_raw(csr, x, src_scale=None, dst_scale=None, bias=None, flags=0, out=None, tag='spmm'):
     lib = L.load()
     if x.dim() != 2 or x.stride(1) != 1:
         x = x.contiguous()
@@ -179,6 +184,9 @@ def _spmm_raw(csr, x, src_scale=None, dst_scale=None, bias=None, flags=0, out=No
         if t is not None and (t.numel() != n or t.dtype != th.float32):
             raise ValueError('spmm: %s must be fp32 with %d elements' % (nm, n))
     args = (L.ptr(csr.indptr), L.ptr(csr.indices), L.ptr(csr.vals), L.ptr(src_scale), L.ptr(dst_scale), L.ptr(bias))
+    if PROFILE is not None:
+        ev0, ev1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        ev0.record()
     if x.dtype == th.float32:
         rc = lib.dg_spmm_csr_f32(*args, x.data_ptr() if x.is_cuda else L.ptr(x), x.stride(0), L.ptr(out),
                                  out.stride(0), csr.n_rows, d, flags, L.stream())
@@ -188,6 +196,9 @@ def _spmm_raw(csr, x, src_scale=None, dst_scale=None, bias=None, flags=0, out=No
     else:
         raise TypeError('spmm: x must be float32 or bfloat16')
     L.check(rc, 'spmm_csr')
+    if PROFILE is not None:
+        ev1.record()
+        PROFILE.append((tag, csr.nnz, csr.n_rows, csr.n_cols, d, x.element_size(), csr.vals is not None, ev0, ev1))
     return out
 
 
@@ -195,9 +206,9 @@ class SpMMFunction(th.autograd.Function):
     """out = act(dst_scale * (A_vals @ (src_scale * x)) + bias); grad flows to x and bias only."""
 
     @staticmethod
-    def forward(ctx, x, bias, csr, src_scale, dst_scale, relu):
-        out = _spmm_raw(csr, x, src_scale, dst_scale, bias, SPMM_RELU if relu else 0)
-        ctx.csr, ctx.relu, ctx.has_bias = csr, relu, bias is not None
+    def forward(ctx, x, bias, csr, src_scale, dst_scale, relu, tag):
+        out = _spmm_raw(csr, x, src_scale, dst_scale, bias, SPMM_RELU if relu else 0, tag=tag)
+        ctx.csr, ctx.relu, ctx.has_bias, ctx.tag = csr, relu, bias is not None, tag
         ctx.save_for_backward(src_scale, dst_scale, out if relu else None)
         ctx.x_dtype = x.dtype
         return out
@@ -212,16 +223,18 @@ class SpMMFunction(th.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             # d x[j] = src_scale[j] * sum_{i : j in row i} vals * dst_scale[i] * dout[i]  -> transposed CSR
-            dx = _spmm_raw(ctx.csr.transpose(), dout, dst_scale, src_scale, None, 0)
+            if ctx.x_dtype == th.bfloat16:
+                dout = dout.to(th.bfloat16)          # bf16 storage path: gather the gradient rows in bf16 too
+            dx = _spmm_raw(ctx.csr.transpose(), dout, dst_scale, src_scale, None, 0, tag=ctx.tag + '.bwd')
             if ctx.x_dtype != th.float32:
                 dx = dx.to(ctx.x_dtype)
-        return dx, dbias, None, None, None, None
+        return dx, dbias, None, None, None, None, None
 
 
-def spmm(csr, x, src_scale=None, dst_scale=None, bias=None, relu=False):
+def spmm(csr, x, src_scale=None, dst_scale=None, bias=None, relu=False, tag='spmm'):
     if not x.is_cuda:
         raise RuntimeError('dreamgnn_b200.spmm needs CUDA tensors (no CPU fallback)')
-    return SpMMFunction.apply(x, bias, csr, src_scale, dst_scale, relu)
+    return SpMMFunction.apply(x, bias, csr, src_scale, dst_scale, relu, tag)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -297,8 +310,8 @@ class DecoderFunction(th.autograd.Function):
                                        L.ptr(dz1), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3), L.ptr(ws),
                                        ws.numel(), L.stream()), 'decoder_bwd')
         # scatter of dz1 into node gradients = two segment sums in fixed order (no atomics)
-        dpd = _spmm_raw(pairs.by_src(), dz1) if ctx.needs_input_grad[0] else None
-        dps = _spmm_raw(pairs.by_dst(), dz1) if ctx.needs_input_grad[1] else None
+        dpd = _spmm_raw(pairs.by_src(), dz1, tag='decoder.seg') if ctx.needs_input_grad[0] else None
+        dps = _spmm_raw(pairs.by_dst(), dz1, tag='decoder.seg') if ctx.needs_input_grad[1] else None
         return dpd, dps, dw2, db2, dw3, db3, None, None, None, None
 
 

@@ -1,0 +1,178 @@
+"""Training loop with the reference's flags and `train(args, dataset, cv)` signature
+(train.py:154-395 and the argparse block at train.py:402-452), built on the drop-in modules.
+
+`train_iteration` is the unit bench.py times: augmentation (always on, train.py:254-277), forward,
+BCE + beta * common losses (train.py:286-294), backward, clip_grad_norm_, Adam step (train.py:297-300).
+"""
+import argparse
+import os
+import time
+
+import torch as th
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .augmentation import augment_graph_data
+from .model import Net
+from .utils import common_loss, common_loss_gram, setup_seed  # noqa: F401
+
+FIXED_SEEDS = [77, 31415, 888, 1001, 9999, 0, 42, 123, 2024, 7]      # train.py:456
+
+
+class LabelSmoothingBCELoss(nn.Module):
+    """train.py:15-23."""
+
+    def __init__(self, smoothing=0.0):
+        super().__init__()
+        self.smoothing = smoothing
+
+    def forward(self, pred, target):
+        return F.binary_cross_entropy_with_logits(pred, target * (1 - self.smoothing) + self.smoothing * 0.5)
+
+
+def build_parser():
+    """The reference's 36 flags with the same names, types, defaults and quirks (train.py:404-450)."""
+    p = argparse.ArgumentParser(description='DREAM-GNN (B200-native hot path)')
+    p.add_argument('--device', default='0', type=int)
+    p.add_argument('--save_dir', type=str)
+    p.add_argument('--save_id', type=int)
+    p.add_argument('--model_activation', type=str, default='leaky')
+    p.add_argument('--dropout', type=float, default=0.3)
+    p.add_argument('--gcn_agg_units', type=int, default=1024)
+    p.add_argument('--gcn_agg_accum', type=str, default='sum')
+    p.add_argument('--gcn_out_units', type=int, default=128)
+    p.add_argument('--train_max_iter', type=int, default=18000)
+    p.add_argument('--train_grad_clip', type=float, default=1.0)
+    p.add_argument('--train_valid_interval', type=int, default=250)
+    p.add_argument('--gcn_agg_norm_symm', type=bool, default=True)
+    p.add_argument('--nhid1', type=int, default=768)
+    p.add_argument('--nhid2', type=int, default=128)
+    p.add_argument('--train_lr', type=float, default=0.002)
+    p.add_argument('--layers', type=int, default=3)
+    p.add_argument('--share_param', default=True, action='store_true')
+    p.add_argument('--data_name', default='Gdataset', type=str)
+    p.add_argument('--num_neighbor', type=int, default=4)
+    p.add_argument('--beta', type=float, default=0.001)
+    p.add_argument('--weight_decay', type=float, default=1e-5)
+    p.add_argument('--l2_reg_weight', type=float, default=0.0)
+    p.add_argument('--attention_dropout', type=float, default=0.1)
+    p.add_argument('--embedding_mode', type=str, default='pretrained', choices=['pretrained', 'random'])
+    p.add_argument('--use_augmentation', action='store_true', default=False)
+    p.add_argument('--aug_methods', type=str, nargs='+', default=['edge_dropout', 'feature_noise'],
+                   choices=['edge_dropout', 'add_random_edges', 'feature_noise', 'graph_noise', 'feature_masking',
+                            'mix_up'])
+    p.add_argument('--edge_dropout_rate', type=float, default=0.1)
+    p.add_argument('--add_edge_rate', type=float, default=0.03)
+    p.add_argument('--feature_noise_scale', type=float, default=0.05)
+    p.add_argument('--graph_noise_scale', type=float, default=0.03)
+    p.add_argument('--feature_mask_rate', type=float, default=0.1)
+    p.add_argument('--mixup_alpha', type=float, default=0.2)
+    p.add_argument('--save_model', action='store_true')
+    p.add_argument('--label_smoothing', type=float, default=0.0)
+    p.add_argument('--generate_top_predictions', action='store_true', default=False)
+    p.add_argument('--top_k', type=int, default=200)
+    p.set_defaults(use_gate_attention=False)
+    return p
+
+
+def aug_params_from_args(args):
+    """train.py:237-245."""
+    g = lambda k, d: getattr(args, k, d)
+    return {'edge_dropout_rate': g('edge_dropout_rate', 0.1), 'feature_noise_scale': g('feature_noise_scale', 0.05),
+            'graph_noise_scale': g('graph_noise_scale', 0.02), 'add_edge_rate': g('add_edge_rate', 0.03),
+            'feature_mask_rate': g('feature_mask_rate', 0.1), 'mixup_alpha': g('mixup_alpha', 0.2)}
+
+
+class TrainState:
+    """Device-resident inputs of one fold's training loop (what train.py:172-204 prepares)."""
+
+    def __init__(self, enc_graph, dec_graph, labels, drug_graph, dis_graph, drug_feature_graph, disease_feature_graph,
+                 drug_feat, dis_feat, drug_sim_feat, dis_sim_feat):
+        self.enc_graph, self.dec_graph, self.labels = enc_graph, dec_graph, labels
+        self.drug_graph, self.dis_graph = drug_graph, dis_graph
+        self.drug_feature_graph, self.disease_feature_graph = drug_feature_graph, disease_feature_graph
+        self.drug_feat, self.dis_feat = drug_feat, dis_feat
+        self.drug_sim_feat, self.dis_sim_feat = drug_sim_feat, dis_sim_feat
+
+
+def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_params, beta=0.001, grad_clip=1.0,
+                    common_loss_fn=common_loss):
+    """One training iteration exactly as train.py:250-300; returns the (device) loss tensor."""
+    model.train()
+    aug = augment_graph_data({
+        'enc_graph': state.enc_graph, 'drug_graph': state.drug_graph, 'disease_graph': state.dis_graph,
+        'drug_feature_graph': state.drug_feature_graph, 'disease_feature_graph': state.disease_feature_graph,
+        'drug_feat': state.drug_feat, 'disease_feat': state.dis_feat,
+        'drug_sim_feat': state.drug_sim_feat, 'disease_sim_feat': state.dis_sim_feat}, aug_methods, aug_params)
+    pred, drug_out, drug_sim_out, dis_out, dis_sim_out = model(
+        aug['enc_graph'], state.dec_graph, aug['drug_graph'], aug['drug_sim_feat'], aug['drug_feat'],
+        aug['disease_graph'], aug['disease_sim_feat'], aug['disease_feat'], aug['drug_feature_graph'],
+        aug['disease_feature_graph'], False)
+    rel = rel_loss_fn(pred.squeeze(-1), state.labels)
+    total = rel + beta * (common_loss_fn(drug_out, drug_sim_out) + common_loss_fn(dis_out, dis_sim_out))
+    optimizer.zero_grad()
+    total.backward()
+    nn.utils.clip_grad_norm_(model.parameters(), grad_clip)
+    optimizer.step()
+    return total
+
+
+def train(args, dataset, cv):
+    """Mirror of train.py:154-395: one fold. `dataset` must expose the reference loader's attributes
+    (`drug_feature`, `disease_feature`, `*_feature_shape`, `drug_sim_features`, `disease_sim_features`,
+    `cv_data_dict`, `data_cv`, `cv_specific_graphs`) with graphs built by dreamgnn_b200.graph_build."""
+    from .evaluation import evaluate
+    args.src_in_units = dataset.drug_feature_shape[1]
+    args.dst_in_units = dataset.disease_feature_shape[1]
+    args.fdim_drug = dataset.drug_feature_shape[0]
+    args.fdim_disease = dataset.disease_feature_shape[0]
+    args.rating_vals = dataset.cv_data_dict[cv][2]
+    cv_data = dataset.data_cv[cv]
+    graphs = dataset.cv_specific_graphs[cv]
+    dev = args.device
+    state = TrainState(
+        cv_data['train'][0].int().to(dev), cv_data['train'][1].int().to(dev), cv_data['train'][2].to(dev),
+        graphs['drug_graph'].to(dev), graphs['disease_graph'].to(dev), graphs['drug_feature_graph'].to(dev),
+        graphs['disease_feature_graph'].to(dev), dataset.drug_feature.to(dev), dataset.disease_feature.to(dev),
+        th.as_tensor(dataset.drug_sim_features, dtype=th.float32).to(dev),
+        th.as_tensor(dataset.disease_sim_features, dtype=th.float32).to(dev))
+    train_data_dict, test_data_dict = {'test': cv_data['train']}, {'test': cv_data['test']}
+    model = Net(args=args).to(dev)
+    if getattr(args, 'label_smoothing', 0.0) > 0:
+        rel_loss_fn = LabelSmoothingBCELoss(smoothing=args.label_smoothing)
+    else:
+        rel_loss_fn = nn.BCEWithLogitsLoss()
+    optimizer = th.optim.Adam(model.parameters(), lr=args.train_lr, weight_decay=args.weight_decay)
+    scheduler = th.optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'max', patience=500, factor=0.5)
+    aug_methods = getattr(args, 'aug_methods', ['edge_dropout', 'feature_noise'])
+    aug_params = aug_params_from_args(args)
+    log_path = os.path.join(args.save_dir, 'test_metric%s.csv' % args.save_id)
+    log = open(log_path, 'w')
+    log.write('iter,loss,train_auroc,train_aupr,test_auroc,test_aupr\n')
+    best = dict(aupr=-1.0, auroc=0.0, it=0, train_aupr=0.0, train_auroc=0.0)
+    start = time.perf_counter()
+    for it in range(1, args.train_max_iter):
+        total = train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_params, args.beta,
+                                args.train_grad_clip)
+        if it % args.train_valid_interval == 0:
+            ev = lambda d: evaluate(args, model, d, state.drug_graph, state.drug_feat, state.drug_sim_feat,
+                                    state.dis_graph, state.dis_feat, state.dis_sim_feat, state.drug_feature_graph,
+                                    state.disease_feature_graph)
+            tr_auroc, tr_aupr = ev(train_data_dict)
+            te_auroc, te_aupr = ev(test_data_dict)
+            scheduler.step(te_aupr)
+            log.write('%d,%.4f,%.4f,%.4f,%.4f,%.4f\n' % (it, total.item(), tr_auroc, tr_aupr, te_auroc, te_aupr))
+            log.flush()
+            print('Iter=%5d, Loss=%.4f, Train: AUROC=%.4f, AUPR=%.4f, Test: AUROC=%.4f, AUPR=%.4f'
+                  % (it, total.item(), tr_auroc, tr_aupr, te_auroc, te_aupr))
+            if te_aupr > best['aupr']:
+                best.update(aupr=te_aupr, auroc=te_auroc, it=it, train_aupr=tr_aupr, train_auroc=tr_auroc)
+                if getattr(args, 'save_model', False):
+                    th.save(model.state_dict(), os.path.join(args.save_dir, 'best_model_fold%s.pth' % args.save_id))
+    log.close()
+    print('Running time:', time.strftime('%H:%M:%S', time.gmtime(round(time.perf_counter() - start))))
+    with open(os.path.join(args.save_dir, 'best_metric%s.csv' % args.save_id), 'w') as f:
+        f.write('iter,train_auroc,train_aupr,test_auroc,test_aupr\n')
+        f.write('%d,%.4f,%.4f,%.4f,%.4f\n' % (best['it'], best['train_auroc'], best['train_aupr'], best['auroc'],
+                                                best['aupr']))
+    return best['auroc'], best['aupr']
