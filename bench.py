@@ -16,7 +16,6 @@ region is bracketed by barrier + synchronize and the reported time is the max ov
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -42,53 +41,61 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-
-    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (a light in-process
+    thread: spawning nvidia-smi next to the timed loop stalls kernel launches for hundreds of ms)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                       # noqa: BLE001
+            self.nv, self.err = None, str(e)
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [v for v in vis.split(',') if v.strip() != '']
+            if index < len(ids) and ids[index].strip().isdigit():
+                return int(ids[index])
+        return index
+
+    def _loop(self):
+        nv = self.nv
+        bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:                        # noqa: BLE001
+                pass
+            self._stop.wait(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(',')]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(nm)
-        sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+        if self.nv is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + getattr(self, 'err', '')]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        sm = sorted(self.samples)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(sm)}
 
 
 def spmm_algorithmic_bytes(nnz, n_rows, n_cols, d, elem, valued):
@@ -152,11 +159,16 @@ def run_b200(args):
     _lib.reset_launch_count()
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = os.environ.get('DG_PROFILE_RANGE') == '1'       # ncu --profile-from-start off
+    if prof_range:
+        th.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         loss = step()
     e1.record()
     barrier()
+    if prof_range:
+        th.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count()
     log, ops.PROFILE = ops.PROFILE, None

@@ -12,6 +12,7 @@
 // them kUnroll at a time: all loads of the group are issued before any FMA so kUnroll*NCHUNK
 // 128-bit requests per lane are in flight. HBM/L2-bound integer-indexed gather: no tensor cores.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -42,8 +43,8 @@ struct LoadBF16 {
   }
 };
 
-template <typename L, int NCHUNK, int kUnroll, bool kWeighted>
-__global__ void __launch_bounds__(256)
+template <typename L, int NCHUNK, int kUnroll, bool kWeighted, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ vals,
                 const float* __restrict__ src_scale, const float* __restrict__ dst_scale,
                 const float* __restrict__ bias, const typename L::Elem* __restrict__ x, int64_t ldx,
@@ -67,16 +68,28 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
   }
 
   const int beg = indptr[row], end = indptr[row + 1];
+  // software prefetch of the next 32 (column, weight) pairs: the index load, and the dependent gather
+  // of src_scale[column], are issued one batch ahead so neither latency sits in front of the row loads
+  int j_nx = 0;
+  float w_nx = 0.f, sc_nx = 1.f;
+  if (beg + lane < end) {
+    j_nx = ldg_i32_stream(indices + beg + lane);
+    if (kWeighted) {
+      w_nx = vals ? vals[beg + lane] : 1.f;
+      if (src_scale) sc_nx = src_scale[j_nx];
+    }
+  }
   for (int base = beg; base < end; base += 32) {
-    const int s = base + lane;
-    int j = 0;
-    float w = 0.f;
-    if (s < end) {
-      j = ldg_i32_stream(indices + s);
-      if (kWeighted) {
-        w = vals ? vals[s] : 1.f;
-        if (src_scale) w *= src_scale[j];
-      }
+    const int j = j_nx;
+    const float w = kWeighted ? w_nx * sc_nx : 0.f;
+    const int sn = base + 32 + lane;
+    const bool has_next = sn < end;
+    j_nx = 0;
+    if (has_next) {
+      j_nx = ldg_i32_stream(indices + sn);
+      if (kWeighted) w_nx = vals ? vals[sn] : 1.f;
+    } else if (kWeighted) {
+      w_nx = 0.f;
     }
     const int cnt = min(32, end - base);
     int t = 0;
@@ -86,11 +99,14 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int jj = __shfl_sync(kFull, j, t + u);
-        if (kWeighted) wt[u] = __shfl_sync(kFull, w, t + u);
         const typename L::Elem* xr = x + static_cast<int64_t>(jj) * ldx + col0;
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c)
           if (live[c]) buf[u][c] = L::load(xr + c * 32 * V);
+      }
+      if (kWeighted) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) wt[u] = __shfl_sync(kFull, w, t + u);
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
@@ -116,6 +132,7 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
           for (int v = 0; v < V; ++v) acc[c][v] = kWeighted ? fmaf(wt, b[v], acc[c][v]) : acc[c][v] + b[v];
         }
     }
+    if (kWeighted) sc_nx = (src_scale && has_next) ? src_scale[j_nx] : 1.f;   // next batch's scale, index has landed by now
   }
 
   const float ds = dst_scale ? dst_scale[row] : 1.f;
@@ -144,7 +161,7 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
   }
 }
 
-template <typename L, int NCHUNK, int kUnroll>
+template <typename L, int NCHUNK, int kUnroll, int kMinBlocks>
 static int launch_spmm(const int* indptr, const int* indices, const float* vals, const float* src_scale,
                        const float* dst_scale, const float* bias, const typename L::Elem* x, int64_t ldx, float* out,
                        int64_t ldo, int64_t n_rows, int d, int flags, cudaStream_t st) {
@@ -154,14 +171,23 @@ static int launch_spmm(const int* indptr, const int* indices, const float* vals,
   const int64_t blocks = (warps + 7) / 8;
   if (blocks > 0x7fffffffLL) { set_error("spmm: grid too large"); return DG_ERR_INVALID_ARGUMENT; }
   if (vals || src_scale)
-    spmm_csr_kernel<L, NCHUNK, kUnroll, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    spmm_csr_kernel<L, NCHUNK, kUnroll, true, kMinBlocks><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
         indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
   else
-    spmm_csr_kernel<L, NCHUNK, kUnroll, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    spmm_csr_kernel<L, NCHUNK, kUnroll, false, kMinBlocks><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
         indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
   DG_CHECK_LAUNCH("spmm_csr");
   return DG_OK;
 }
+
+// Tuning knob for experiments only (scripts/spmm_bench.py): DG_SPMM_VARIANT=<n> picks another
+// (unroll, resident blocks) point; unset = the measured best.
+static int spmm_variant() {
+  const char* e = getenv("DG_SPMM_VARIANT");
+  return e ? atoi(e) : 0;
+}
+
+#define DG_SPMM_ARGS indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, dd, flags, st
 
 template <typename L>
 static int spmm_dispatch(const int* indptr, const int* indices, const float* vals, const float* src_scale,
@@ -181,10 +207,29 @@ static int spmm_dispatch(const int* indptr, const int* indices, const float* val
   // pick the slab shape with the least lane waste: d <= 32V -> 1 chunk, <= 64V -> 2, else 3-chunk slabs
   const int per = 32 * L::kVec;
   const int dd = static_cast<int>(d);
-  if (dd <= per) return launch_spmm<L, 1, 8>(indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, dd, flags, st);
-  if (dd <= 2 * per || (dd > 3 * per && dd % (3 * per) && dd % (2 * per) == 0))
-    return launch_spmm<L, 2, 4>(indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, dd, flags, st);
-  return launch_spmm<L, 3, 4>(indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, dd, flags, st);
+  const int var = spmm_variant();
+  if (dd <= per) {
+    switch (var) {
+      case 1: return launch_spmm<L, 1, 4, 6>(DG_SPMM_ARGS);
+      case 2: return launch_spmm<L, 1, 8, 4>(DG_SPMM_ARGS);
+      case 3: return launch_spmm<L, 1, 16, 2>(DG_SPMM_ARGS);
+      default: return launch_spmm<L, 1, 8, 3>(DG_SPMM_ARGS);
+    }
+  }
+  if (dd <= 2 * per || (dd > 3 * per && dd % (3 * per) && dd % (2 * per) == 0)) {
+    switch (var) {
+      case 1: return launch_spmm<L, 2, 2, 5>(DG_SPMM_ARGS);
+      case 2: return launch_spmm<L, 2, 4, 4>(DG_SPMM_ARGS);
+      default: return launch_spmm<L, 2, 4, 3>(DG_SPMM_ARGS);
+    }
+  }
+  switch (var) {
+    case 1: return launch_spmm<L, 3, 2, 4>(DG_SPMM_ARGS);
+    case 2: return launch_spmm<L, 3, 3, 3>(DG_SPMM_ARGS);
+    case 3: return launch_spmm<L, 3, 4, 3>(DG_SPMM_ARGS);
+    case 4: return launch_spmm<L, 3, 1, 6>(DG_SPMM_ARGS);
+    default: return launch_spmm<L, 3, 4, 2>(DG_SPMM_ARGS);
+  }
 }
 
 }  // namespace dg

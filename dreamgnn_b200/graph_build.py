@@ -40,7 +40,7 @@ def generate_enc_graph(rating_pairs, rating_values, num_drug, num_disease, devic
     value, edge order = pair order, and `ci` / `cj` = 1/sqrt(total degree) as [N,1] fp32 node data."""
     device = th.device(device)
     row, col = _dev_index(rating_pairs[0], device), _dev_index(rating_pairs[1], device)
-    vals = th.as_tensor(np.asarray(rating_values)).to(device)
+    vals = (rating_values if isinstance(rating_values, th.Tensor) else th.as_tensor(np.asarray(rating_values))).to(device)
     data = {}
     for rating in th.unique(vals).tolist():                    # np.unique order: ascending
         sel = vals == rating
@@ -55,8 +55,8 @@ def generate_enc_graph(rating_pairs, rating_values, num_drug, num_disease, devic
         dis_ci = dis_blk.csr.degree_norm().unsqueeze(1)
         if symm:
             # out-degree over all etypes = row lengths of the other block's transpose, summed over relations
-            drug_out = dis_blk.csr.transpose().degrees().view(num_drug, dis_blk.num_rel).sum(1)
-            dis_out = drug_blk.csr.transpose().degrees().view(num_disease, drug_blk.num_rel).sum(1)
+            drug_out = dis_blk.csr.transpose().degrees().view(dis_blk.num_rel, num_drug).sum(0)
+            dis_out = drug_blk.csr.transpose().degrees().view(drug_blk.num_rel, num_disease).sum(0)
             drug_cj = _norm_from_degrees(drug_out).unsqueeze(1)
             dis_cj = _norm_from_degrees(dis_out).unsqueeze(1)
         else:

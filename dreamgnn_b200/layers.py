@@ -4,7 +4,7 @@ behind `dreamgnn_b200.ops`. Citations are into /root/reference/layers.py.
 
 What changes underneath:
   * GCMCLayer (layers.py:18-143): one projection GEMM per node type produces the messages of all R
-    relations side by side ([N_src, R*D]); one SpMM launch per destination type walks the combined
+    relations in one [R, N_src, D] buffer; one SpMM launch per destination type walks the combined
     relation-block CSR with `dropout(cj)[src]` and `ci[dst]` fused, i.e. HeteroGraphConv's
     per-etype update_all + stack/sum (K2-K6 in SURVEY.md) become GEMM + SpMM. Backward is the same
     SpMM on the transposed block -- deterministic, no atomics.
@@ -201,14 +201,14 @@ class GCMCLayer(nn.Module):
             x = feats[blk.src_type]
             if x.size(0) != blk.n_src:
                 raise ValueError('%s features have %d rows for %d nodes' % (blk.src_type, x.size(0), blk.n_src))
-            wcat = th.cat([_pad_cols(weights[c[1]], mult) for c in blk.etypes], dim=1)      # [in, R*Dp]
-            h = th.mm(x, wcat)                                                              # all relations at once
-            dp = wcat.shape[1] // blk.num_rel
+            wstack = th.stack([_pad_cols(weights[c[1]], mult) for c in blk.etypes], dim=0)   # [R, in, Dp]
+            h = th.matmul(x.unsqueeze(0), wstack)                    # [R, N_src, Dp]: all relations' messages
+            dp = wstack.shape[2]
             cj = graph.nodes[blk.src_type].data['cj']
-            scale = th.stack([_flat_f32(self.conv.mods[c[1]].dropout(cj)) for c in blk.etypes], dim=1).reshape(-1)
+            scale = th.stack([_flat_f32(self.conv.mods[c[1]].dropout(cj)) for c in blk.etypes], dim=0).reshape(-1)
             if MESSAGE_DTYPE != th.float32:
                 h = h.to(MESSAGE_DTYPE)
-            agg = ops.spmm(blk.csr, h.view(blk.n_src * blk.num_rel, dp), src_scale=scale,
+            agg = ops.spmm(blk.csr, h.reshape(blk.num_rel * blk.n_src, dp), src_scale=scale,
                            dst_scale=_flat_f32(graph.nodes[dst_type].data['ci']), tag='gcmc')
             out[dst_type] = agg[:, :D] if dp != D else agg
         drug = self.dropout(self.agg_act(out['drug']))

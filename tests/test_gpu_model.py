@@ -75,10 +75,10 @@ def test_graph_construction_bit_exact(case):
             np.testing.assert_array_equal(enc.nodes[nt].data['cj'].cpu().numpy(), g[f'{split}.cj.{nt}'])
         s, d = dec.edges()
         np.testing.assert_array_equal(np.stack([s.cpu().numpy(), d.cpu().numpy()]), g[f'{split}.pairs'])
-        # relation-block CSR == oracle CSR of the combined (dst, src*R + r) pairs
+        # relation-block CSR == oracle CSR of the combined (dst, r*N_src + src) pairs
         blk = enc.block('disease')
         rows = np.concatenate([g[f'{split}.enc.0'][1], g[f'{split}.enc.1'][1]])
-        cols = np.concatenate([g[f'{split}.enc.0'][0] * 2, g[f'{split}.enc.1'][0] * 2 + 1])
+        cols = np.concatenate([g[f'{split}.enc.0'][0], g[f'{split}.enc.1'][0] + blk.n_src])
         indptr, indices, eid = R.csr_from_pairs(rows, cols, blk.n_dst)
         np.testing.assert_array_equal(blk.csr.indptr.cpu().numpy(), indptr)
         np.testing.assert_array_equal(blk.csr.indices.cpu().numpy(), indices)
