@@ -1,0 +1,93 @@
+"""GPU: the DrugDataLoader mirror and train() end to end on a synthetic `.mat` of the reference's schema,
+against the golden vectors the reference produced from the same file."""
+import argparse
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.io as sio
+import torch as th
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def loaded():
+    from dreamgnn_b200 import _lib
+    from dreamgnn_b200.data_loader import DrugDataLoader
+    _lib.load()
+    g = H.load_golden('tinyA')
+    root = tempfile.mkdtemp(prefix='dg_mat_')
+    d = os.path.join(root, 'raw_data', 'drug_data', 'lrssl')
+    os.makedirs(d)
+    names = np.empty((60, 1), dtype=object)
+    for i in range(60):
+        names[i, 0] = np.array(['DB%05d' % i])
+    sio.savemat(os.path.join(d, 'lrssl.mat'), {'didr': g['mat.didr'], 'drug': g['mat.drug'], 'disease': g['mat.disease'],
+                                               'drug_embed': g['mat.drug_embed'], 'disease_embed': g['mat.disease_embed'],
+                                               'Wrname': names})
+    old = os.getcwd()
+    os.chdir(root)
+    try:
+        ds = DrugDataLoader('lrssl', 'cuda:0', symm=True, k=int(g['k']))
+    finally:
+        os.chdir(old)
+    return root, g, ds
+
+
+def test_loader_matches_reference_fold0(loaded):
+    _, g, ds = loaded
+    assert ds.num_drug == 60 and ds.num_disease == 45 and len(ds.data_cv) == 10
+    for split in ('train', 'test'):
+        enc, dec, labels = ds.data_cv[0][split]
+        s, d = dec.edges()
+        np.testing.assert_array_equal(np.stack([s.cpu().numpy(), d.cpu().numpy()]), g[f'{split}.pairs'])
+        np.testing.assert_array_equal(labels.numpy(), g[f'{split}.labels'])
+        for nt in ('drug', 'disease'):
+            np.testing.assert_array_equal(enc.nodes[nt].data['ci'].cpu().numpy(), g[f'{split}.ci.{nt}'])
+    np.testing.assert_array_equal(ds.drug_feature.cpu().numpy(), g['feat.drug'])
+    for key in H.KNN_KEYS:
+        t = ds.cv_specific_graphs[3][key]
+        gr, gc, gv = H.canon_coo(g[f'knn.{key}.indices'][0], g[f'knn.{key}.indices'][1], g[f'knn.{key}.values'])
+        np.testing.assert_array_equal(t._indices().cpu().numpy(), np.stack([gr, gc]))
+        np.testing.assert_array_equal(t._values().cpu().numpy(), gv)
+
+
+def test_train_runs_and_evaluates(loaded):
+    """train() with the reference's flags: finite loss, AUROC/AUPR in range, result files written; and with
+    all randomness off the evaluation equals the oracle's on the same weights (<= 1e-3, north_star)."""
+    from dreamgnn_b200.train import build_parser, train
+    from dreamgnn_b200.evaluation import evaluate
+    from dreamgnn_b200.model import Net
+    from oracle import restate as R
+    root, g, ds = loaded
+    args = build_parser().parse_args(['--data_name', 'lrssl', '--train_max_iter', '7', '--train_valid_interval', '3',
+                                      '--gcn_agg_units', '105', '--gcn_out_units', '16', '--nhid1', '40', '--nhid2', '16',
+                                      '--num_neighbor', '4'])
+    args.device, args.save_dir, args.save_id = 'cuda:0', root, 1
+    th.manual_seed(77)
+    auroc, aupr = train(args, ds, 0)
+    assert 0.0 <= auroc <= 1.0 and 0.0 <= aupr <= 1.0
+    assert os.path.isfile(os.path.join(root, 'test_metric1.csv')) and os.path.isfile(os.path.join(root, 'best_metric1.csv'))
+    log = open(os.path.join(root, 'test_metric1.csv')).read().splitlines()
+    assert len(log) == 3 and all(np.isfinite(float(r.split(',')[1])) for r in log[1:])
+    # evaluation parity on fixed weights
+    margs = argparse.Namespace(**vars(args))
+    margs.rating_vals, margs.src_in_units, margs.dst_in_units = [0, 1], 48, 48
+    margs.fdim_drug, margs.fdim_disease = 60, 45
+    net = Net(margs)
+    net.load_state_dict({k[3:]: th.tensor(v) for k, v in g.items() if k.startswith('sd.')})
+    net = net.to('cuda:0')
+    gr = ds.cv_specific_graphs[0]
+    dsim = th.as_tensor(ds.drug_sim_features, dtype=th.float32).cuda()
+    ssim = th.as_tensor(ds.disease_sim_features, dtype=th.float32).cuda()
+    a, p = evaluate(args, net, {'test': ds.data_cv[0]['test']}, gr['drug_graph'], ds.drug_feature, dsim,
+                    gr['disease_graph'], ds.disease_feature, ssim, gr['drug_feature_graph'], gr['disease_feature_graph'])
+    inp = H.net_inputs(g, 'test')
+    knn = [inp['drug_graph'], inp['dis_graph'], inp['drug_feature_graph'], inp['dis_feature_graph']]
+    feats = (inp['drug_feat'], inp['dis_feat'], inp['drug_sim_feat'], inp['dis_sim_feat'])
+    ra, rp = R.evaluate_auc(H.params(g), inp['enc_graph'], inp['dec_pairs'], g['test.labels'], knn, feats, dict(layers=3))
+    assert abs(a - ra) <= 1e-3 and abs(p - rp) <= 1e-3
