@@ -46,6 +46,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.period = float(os.environ.get('DG_CLOCK_PERIOD', '0.25'))
         self._stop = threading.Event()
         self.thread = None
         try:
@@ -81,7 +82,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:                        # noqa: BLE001
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(self.period)
 
     def start(self):
         if self.nv is not None:
@@ -159,14 +160,26 @@ def run_b200(args):
     _lib.reset_launch_count()
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     barrier()
+    stats0 = th.cuda.memory_stats(dev)
     prof_range = os.environ.get('DG_PROFILE_RANGE') == '1'       # ncu --profile-from-start off
     if prof_range:
         th.cuda.profiler.start()
     e0.record()
+    marks, host_ms = [], []
     for _ in range(args.steps):
+        t_h = time.perf_counter()
         loss = step()
+        host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
+        ev = th.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
     e1.record()
     barrier()
+    step_ms = [round(a.elapsed_time(b), 2) for a, b in zip([e0] + marks[:-1], marks)]
+    stats1 = th.cuda.memory_stats(dev)
+    alloc_diag = {k: int(stats1.get(k, 0) - stats0.get(k, 0)) for k in ('num_device_alloc', 'num_device_free', 'num_alloc_retries')}
+    alloc_diag['reserved_gb'] = round(stats1.get('reserved_bytes.all.current', 0) / 1e9, 1)
+    alloc_diag['peak_allocated_gb'] = round(stats1.get('allocated_bytes.all.peak', 0) / 1e9, 1)
     if prof_range:
         th.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
@@ -216,6 +229,9 @@ def run_b200(args):
         c['bmin'] += spmm_compulsory_bytes(nnz, nr, nc, d, el, valued)
         c['n'] += 1
         c['nnz'] += nnz
+    per_step = len(log) // max(args.steps, 1)
+    spmm_ms_by_step = [round(sum(r[7].elapsed_time(r[8]) for r in log[i * per_step:(i + 1) * per_step]), 2)
+                       for i in range(args.steps)] if per_step else []
     top_key, top = max(classes.items(), key=lambda kv: kv[1]['ms'])
     peak, peak_src = measured_peak()
     achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
@@ -259,7 +275,7 @@ def run_b200(args):
                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
                    'what': 'features + labels copied from pinned host memory every step, loss read back; graph '
                            'structure stays resident as in the reference training loop (train.py:186-200)'},
-           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
+           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'step_ms': step_ms, 'allocator': alloc_diag, 'host_enqueue_ms': host_ms, 'spmm_ms_by_step': spmm_ms_by_step,
            'final_loss': round(loss_host, 6)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

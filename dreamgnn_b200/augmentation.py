@@ -56,7 +56,7 @@ class GraphAugmentation:
         if not isinstance(sparse_graph, th.Tensor) or not sparse_graph.is_sparse:
             return sparse_graph
         base = adjacency_csr(sparse_graph)
-        if base.slot_order:
+        if base.slot_order and not base.eid_is_slot:
             # output of an earlier dropout: its edge ids still name the grand-parent's entries;
             # renumber to this tensor's own COO positions (= slots) before drawing a new perm
             pos = th.empty(int(base.eid.max()) + 1 if base.nnz else 1, dtype=th.int32, device=base.device)
@@ -65,7 +65,8 @@ class GraphAugmentation:
             nb = ops.CSR(base.indptr, base.indices, pos[base.eid.long()], base.vals, base.n_rows, base.n_cols)
             nt = ops.CSR(t.indptr, t.indices, pos[t.eid.long()], t.vals, t.n_rows, t.n_cols)
             nb._t, nt._t = nt, nb
-            base = nb
+            nb.slot_order = nb.eid_is_slot = True
+            sparse_graph._dg_csr = base = nb
         n = base.nnz
         k = num_keep_edges(n, dropout_rate)
         perm = th.randperm(n, device=sparse_graph.device)

@@ -1,0 +1,415 @@
+// Dense projections on the 5th-generation tensor cores: C[b] = A[b] * B[b]^T with fp32-level accuracy.
+//
+//   * tcgen05.mma.kind::tf32 issued by one elected thread, accumulator in TMEM (128 lanes x 128 columns),
+//     operand tiles (128 rows x 32 fp32 = 128 B, SWIZZLE_128B, K-major) staged in shared memory by TMA,
+//     mbarrier full/empty ring between the TMA warp and the MMA warp, tcgen05.ld epilogue by 4 warps.
+//   * fp32 accuracy from error-compensated TF32 ("3xTF32"): every operand is split once into
+//     hi = rna_tf32(x) and lo = x - hi (exact), and D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulates in the
+//     same TMEM tile; the dropped lo*lo term is ~2^-22 relative. One stage carries the four tiles of a
+//     k-block so A_hi / B_hi are fetched once for two of the three products.
+//   * long-K / small-output shapes (the weight-gradient GEMMs, K = number of nodes) are split along K into
+//     per-CTA partial tiles that a second kernel sums in a fixed order (deterministic, no atomics).
+//
+// Replaces the cuBLAS calls behind th.mm / th.matmul at layers.py:120-121, 220-221 (W_r projections),
+// layers.py:311 (FGCN support = x @ W) and their backward GEMMs.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace dg {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;            // tile; 32 fp32 = one 128-byte swizzle row
+constexpr int kTileBytes = kBM * kBK * 4;                // 16 KB per operand tile
+constexpr int kGemmThreads = 192;                        // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
+constexpr int kTmemCols = 128;
+constexpr uint32_t kSpinLimit = 1u << 22;                // watchdog: trap instead of hanging the GPU
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start>>4 | LBO(ignored)=1 |
+// SBO = 1024 B between 8-row groups | version 1 | layout SWIZZLE_128B (= 2 in bits 61..63)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return static_cast<uint64_t>((addr & 0x3ffff) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = f32 (bits 4-5 = 1), A/B = tf32 (2 at bits 7-9 / 10-12), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kBN >> 3) << 17) | ((kBM >> 4) << 24);
+
+struct GemmParams {
+  float* C;
+  float* partial;          // [batch*splits, M, N] when splits > 1
+  const float* row_scale;  // nullable, [batch * M]
+  int64_t ldc, stride_c;
+  int M, N, nkb, kb_per_split, splits, a_batched, b_batched, vec_ok;
+};
+
+template <bool kSplit3>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const GemmParams p) {
+  constexpr int kTiles = kSplit3 ? 4 : 2;                        // tiles per stage
+  constexpr int kStageBytes = kTiles * kTileBytes;
+  constexpr int kStages = kSplit3 ? 3 : 6;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the dynamic window is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);     // full[kStages], empty[kStages], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const int batch = blockIdx.z / p.splits, split = blockIdx.z - batch * p.splits;
+  const int kb0 = split * p.kb_per_split;
+  const int kb1 = min(p.nkb, kb0 + p.kb_per_split);
+  const int n_iter = kb1 - kb0;
+
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), tfull = smem_u32(bars + 2 * kStages);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                              // TMEM: one warp allocates (and later frees)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(static_cast<uint32_t>(kTmemCols)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane) =====
+    if (lane == 0) {
+      const int za = p.a_batched ? batch : 0, zb = p.b_batched ? batch : 0;
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages, round = it / kStages;
+        mbar_wait(empty0 + 8 * s, (round & 1) ^ 1);
+        const uint32_t dst = smem_u32(smem + s * kStageBytes);
+        const uint32_t bar = full0 + 8 * s;
+        mbar_expect_tx(bar, kStageBytes);
+        const int k = (kb0 + it) * kBK;
+        tma_load_3d(dst, &tmA_hi, bar, k, m0, za);
+        if (kSplit3) {
+          tma_load_3d(dst + kTileBytes, &tmA_lo, bar, k, m0, za);
+          tma_load_3d(dst + 2 * kTileBytes, &tmB_hi, bar, k, n0, zb);
+          tma_load_3d(dst + 3 * kTileBytes, &tmB_lo, bar, k, n0, zb);
+        } else {
+          tma_load_3d(dst + kTileBytes, &tmB_hi, bar, k, n0, zb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages, round = it / kStages;
+        mbar_wait(full0 + 8 * s, round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = smem_u32(smem + s * kStageBytes);
+        const uint64_t a_hi = smem_desc_sw128(base);
+        const uint64_t a_lo = smem_desc_sw128(base + kTileBytes);
+        const uint64_t b_hi = smem_desc_sw128(base + (kSplit3 ? 2 : 1) * kTileBytes);
+        const uint64_t b_lo = smem_desc_sw128(base + 3 * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {                     // UMMA_K = 8 tf32 = 32 bytes -> +2 in the address field
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          if (kSplit3) {
+            // small terms first, the dominant product last
+            umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, kInstrDesc, acc);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, kInstrDesc, 1u);
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, kInstrDesc, 1u);
+          } else {
+            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, kInstrDesc, acc);
+          }
+        }
+        umma_commit(empty0 + 8 * s);                            // frees the stage once these MMAs retire
+      }
+      umma_commit(tfull);                                       // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global; warp w owns TMEM lanes 32*(w%4) .. +31 =====
+    const int q = warp & 3;
+    if (n_iter > 0) {
+      mbar_wait(tfull, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const int row = m0 + q * 32 + lane;
+    float scale = 1.f;
+    float* out;
+    int64_t ld;
+    if (p.splits > 1) {
+      out = p.partial + (static_cast<int64_t>(blockIdx.z) * p.M + row) * p.N;
+      ld = p.N;
+    } else {
+      out = p.C + batch * p.stride_c + static_cast<int64_t>(row) * p.ldc;
+      ld = p.ldc;
+      if (p.row_scale && row < p.M) scale = p.row_scale[static_cast<int64_t>(batch) * p.M + row];
+    }
+    (void)ld;
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      uint32_t v[32];
+      if (n_iter > 0) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const int col0 = n0 + c * 32;
+      if (row < p.M && col0 < p.N) {
+        if (p.vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out + col0 + j) =
+                make_float4(__uint_as_float(v[j]) * scale, __uint_as_float(v[j + 1]) * scale,
+                            __uint_as_float(v[j + 2]) * scale, __uint_as_float(v[j + 3]) * scale);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) out[col0 + j] = __uint_as_float(v[j]) * scale;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(static_cast<uint32_t>(kTmemCols)));
+  }
+}
+
+// hi = round-to-nearest tf32 (low 13 mantissa bits cleared), lo = x - hi (exact in fp32); packed [rows, kp]
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ld, int64_t batch_stride, int rows, int k, int kp,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = static_cast<int64_t>(rows) * kp;
+  const int64_t b = blockIdx.y;
+  const float* xb = x + b * batch_stride;
+  float* hb = hi + b * total;
+  float* lb = lo ? lo + b * total : nullptr;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / kp;
+    const int c = static_cast<int>(i - r * kp);
+    const float v = c < k ? xb[r * ld + c] : 0.f;
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    const float hf = __uint_as_float(h);
+    hb[i] = hf;
+    if (lb) lb[i] = v - hf;
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float* __restrict__ C,
+                                     int64_t ldc, int64_t stride_c, const float* __restrict__ row_scale) {
+  const int64_t per = static_cast<int64_t>(M) * N;
+  const int b = blockIdx.y;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < per; i += stride) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(static_cast<int64_t>(b) * splits + k) * per + i];   // fixed order
+    const int64_t r = i / N;
+    const int c = static_cast<int>(i - r * N);
+    if (row_scale) s *= row_scale[static_cast<int64_t>(b) * M + r];
+    C[b * stride_c + r * ldc + c] = s;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// packed [batch, rows, kp] fp32 tensor, box = 32 (k) x 128 (rows) x 1, 128-byte swizzle, OOB -> 0
+static int make_map(CUtensorMap* map, const float* base, int rows, int kp, int batch) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("gemm: cuTensorMapEncodeTiled not available from the driver"); return DG_ERR_UNSUPPORTED; }
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(kp), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(kp) * 4, static_cast<cuuint64_t>(kp) * 4 * rows};
+  cuuint32_t box[3] = {kBK, kBM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return DG_ERR_INVALID_ARGUMENT; }
+  return DG_OK;
+}
+
+struct GemmPlan {
+  int kp, nkb, splits, kb_per_split, a_copies, b_copies;
+  size_t a_elems, b_elems, partial_elems;
+};
+
+static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int a_batched, int b_batched) {
+  GemmPlan g;
+  g.kp = static_cast<int>((K + 3) / 4 * 4);
+  g.nkb = static_cast<int>((K + kBK - 1) / kBK);
+  const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN) * batch;
+  int splits = 1;
+  if (tiles < kNumSM && g.nkb >= 16) {                      // small output, long K: split K to fill the SMs
+    splits = static_cast<int>((2 * kNumSM + tiles - 1) / tiles);
+    if (splits > g.nkb / 8) splits = g.nkb / 8;
+    if (splits < 1) splits = 1;
+  }
+  // the tensor-core accumulator truncates when it aligns addends, so its error grows ~linearly with the
+  // number of accumulated terms: cap one TMEM accumulation at 64 k-blocks (K = 2048) and let the fp32
+  // split-K reduction (round-to-nearest) combine the pieces. Measured: 1.8e-6 rel at K=1024, 5e-6 at K=5000.
+  constexpr int kMaxKbPerAccum = 64;
+  if ((g.nkb + splits - 1) / splits > kMaxKbPerAccum) splits = (g.nkb + kMaxKbPerAccum - 1) / kMaxKbPerAccum;
+  g.kb_per_split = (g.nkb + splits - 1) / splits;
+  g.splits = (g.nkb + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
+  g.a_copies = a_batched ? static_cast<int>(batch) : 1;
+  g.b_copies = b_batched ? static_cast<int>(batch) : 1;
+  g.a_elems = static_cast<size_t>(g.a_copies) * M * g.kp;
+  g.b_elems = static_cast<size_t>(g.b_copies) * N * g.kp;
+  g.partial_elems = g.splits > 1 ? static_cast<size_t>(batch) * g.splits * M * N : 0;
+  return g;
+}
+
+}  // namespace dg
+
+extern "C" {
+
+size_t dg_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, int a_batched, int b_batched) {
+  using namespace dg;
+  GemmPlan g = plan_gemm(M, N, K, batch, a_batched, b_batched);
+  size_t b = 0;
+  b = ws_add(b, g.a_elems * 4);
+  b = ws_add(b, g.a_elems * 4);
+  b = ws_add(b, g.b_elems * 4);
+  b = ws_add(b, g.b_elems * 4);
+  b = ws_add(b, g.partial_elems * 4);
+  return b;
+}
+
+int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B, int64_t ldb, int64_t stride_b, float* C,
+                   int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch, const float* row_scale,
+                   int precision, void* workspace, size_t workspace_bytes, dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "M, N, K, batch must be positive");
+  DG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && batch < 65536, "shape too large");
+  DG_REQUIRE(lda >= K && ldb >= K && ldc >= N, "leading dimension too small");
+  DG_REQUIRE(precision == 0 || precision == 1, "precision: 0 = 3xTF32 (fp32-accurate), 1 = single TF32");
+  cudaStream_t st = as_stream(stream);
+  const int a_batched = stride_a != 0 || batch == 1, b_batched = stride_b != 0 || batch == 1;
+  GemmPlan g = plan_gemm(M, N, K, batch, a_batched, b_batched);
+  DG_REQUIRE((N + kBN - 1) / kBN <= 65535 && batch * g.splits <= 65535, "grid too large");
+  const bool split3 = precision == 0;
+  Workspace w(workspace, workspace_bytes);
+  float* a_hi = w.take<float>(g.a_elems);
+  float* a_lo = w.take<float>(g.a_elems);
+  float* b_hi = w.take<float>(g.b_elems);
+  float* b_lo = w.take<float>(g.b_elems);
+  float* partial = g.partial_elems ? w.take<float>(g.partial_elems) : nullptr;
+  if (!a_hi || !a_lo || !b_hi || !b_lo || (g.partial_elems && !partial)) {
+    set_error("gemm: workspace too small");
+    return DG_ERR_WORKSPACE_TOO_SMALL;
+  }
+  {
+    auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return static_cast<unsigned>(b > 148 * 16 ? 148 * 16 : (b ? b : 1)); };
+    split_tf32_kernel<<<dim3(blocks(static_cast<size_t>(M) * g.kp), g.a_copies), 256, 0, st>>>(
+        A, lda, stride_a, static_cast<int>(M), static_cast<int>(K), g.kp, a_hi, split3 ? a_lo : nullptr);
+    DG_CHECK_LAUNCH("split_tf32(A)");
+    split_tf32_kernel<<<dim3(blocks(static_cast<size_t>(N) * g.kp), g.b_copies), 256, 0, st>>>(
+        B, ldb, stride_b, static_cast<int>(N), static_cast<int>(K), g.kp, b_hi, split3 ? b_lo : nullptr);
+    DG_CHECK_LAUNCH("split_tf32(B)");
+  }
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  DG_PROPAGATE(make_map(&mA_hi, a_hi, static_cast<int>(M), g.kp, g.a_copies));
+  DG_PROPAGATE(make_map(&mA_lo, split3 ? a_lo : a_hi, static_cast<int>(M), g.kp, g.a_copies));
+  DG_PROPAGATE(make_map(&mB_hi, b_hi, static_cast<int>(N), g.kp, g.b_copies));
+  DG_PROPAGATE(make_map(&mB_lo, split3 ? b_lo : b_hi, static_cast<int>(N), g.kp, g.b_copies));
+  GemmParams p;
+  p.C = C; p.partial = partial; p.row_scale = row_scale; p.ldc = ldc; p.stride_c = stride_c;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.nkb = g.nkb; p.kb_per_split = g.kb_per_split; p.splits = g.splits;
+  p.a_batched = (a_batched && batch > 1) ? 1 : 0; p.b_batched = (b_batched && batch > 1) ? 1 : 0;
+  p.vec_ok = (g.splits > 1) ? (N % 4 == 0)
+                            : ((ldc % 4 == 0) && (stride_c % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0));
+  const dim3 grid(static_cast<unsigned>((M + kBM - 1) / kBM), static_cast<unsigned>((N + kBN - 1) / kBN),
+                  static_cast<unsigned>(batch * g.splits));
+  const size_t smem = (split3 ? 3 * 4 : 6 * 2) * kTileBytes + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
+  if (split3) {
+    static bool attr = false;
+    if (!attr) { DG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
+    gemm_nt_tf32_kernel<true><<<grid, kGemmThreads, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  } else {
+    static bool attr = false;
+    if (!attr) { DG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
+    gemm_nt_tf32_kernel<false><<<grid, kGemmThreads, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  }
+  DG_CHECK_LAUNCH("gemm_nt_tf32");
+  if (g.splits > 1) {
+    size_t per = static_cast<size_t>(M) * N;
+    unsigned blocks = static_cast<unsigned>((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
+    splitk_reduce_kernel<<<dim3(blocks, static_cast<unsigned>(batch)), 256, 0, st>>>(partial, g.splits, p.M, p.N, C, ldc, stride_c, row_scale);
+    DG_CHECK_LAUNCH("splitk_reduce");
+  }
+  return DG_OK;
+}
+}

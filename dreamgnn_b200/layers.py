@@ -202,7 +202,7 @@ class GCMCLayer(nn.Module):
             if x.size(0) != blk.n_src:
                 raise ValueError('%s features have %d rows for %d nodes' % (blk.src_type, x.size(0), blk.n_src))
             wstack = th.stack([_pad_cols(weights[c[1]], mult) for c in blk.etypes], dim=0)   # [R, in, Dp]
-            h = th.matmul(x.unsqueeze(0), wstack)                    # [R, N_src, Dp]: all relations' messages
+            h = ops.project(x, wstack)                               # [R, N_src, Dp]: all relations' messages
             dp = wstack.shape[2]
             cj = graph.nodes[blk.src_type].data['cj']
             scale = th.stack([_flat_f32(self.conv.mods[c[1]].dropout(cj)) for c in blk.etypes], dim=0).reshape(-1)
@@ -236,7 +236,7 @@ class GraphConvolution(nn.Module):
             self.bias.data.uniform_(-stdv, stdv)
 
     def support(self, input):
-        return th.mm(input, self.weight)
+        return ops.project(input, self.weight.unsqueeze(0))[0]
 
     def aggregate(self, support, adj, relu=False):
         d = support.shape[1]

@@ -66,13 +66,14 @@ class CSR:
     variants of one graph stay consistent.
     """
 
-    __slots__ = ('indptr', 'indices', 'eid', 'vals', 'n_rows', 'n_cols', '_t', 'slot_order')
+    __slots__ = ('indptr', 'indices', 'eid', 'vals', 'n_rows', 'n_cols', '_t', 'slot_order', 'eid_is_slot')
 
     def __init__(self, indptr, indices, eid, vals, n_rows, n_cols):
         self.indptr, self.indices, self.eid, self.vals = indptr, indices, eid, vals
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
         self._t = None
         self.slot_order = False     # True when the owning COO tensor lists its entries in slot order
+        self.eid_is_slot = False    # True when eid[s] == s (ids already name this tensor's own entries)
 
     @property
     def nnz(self):
@@ -353,4 +354,77 @@ def knn_graph_from_neighbors(nbr):
                                             L.ptr(nnz), L.ptr(ws), ws.numel(), L.stream()), 'knn_graph')
     m = int(nnz.item())                      # one sync per graph build (not on the training path)
     csr = CSR(indptr, col[:m].contiguous(), th.arange(m, dtype=I32, device=dev), val[:m].contiguous(), n, n)
+    csr.eid_is_slot = True
     return csr, row[:m].contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# dense projections on the tcgen05 tensor cores (csrc/gemm_tc.cu)
+# ------------------------------------------------------------------------------------------------
+import os as _os
+
+GEMM_MIN_MACS = 1 << 26          # below this the launch + operand split costs more than it saves: cuBLAS via torch
+
+
+def gemm_backend():
+    """'tcgen05' (default) or 'cublas' (DG_GEMM=cublas: the library stand-in, for A/B comparisons)."""
+    return _os.environ.get('DG_GEMM', 'tcgen05')
+
+
+def gemm_nt(a, b, row_scale=None, precision=0):
+    """C[r] = diag(row_scale[r]) * A[r] @ B[r]^T on the tensor cores. a: [M,K] or [R,M,K]; b: [N,K] or [R,N,K]
+    (a 2-D operand is shared by all batches). fp32 in, fp32 out; precision 0 = 3xTF32 (fp32-level accuracy)."""
+    lib = L.load()
+    if a.dtype != th.float32 or b.dtype != th.float32:
+        raise TypeError('gemm_nt: fp32 operands expected')
+    batch = max(a.shape[0] if a.dim() == 3 else 1, b.shape[0] if b.dim() == 3 else 1)
+    a, b = a.contiguous(), b.contiguous()
+    M, K = a.shape[-2], a.shape[-1]
+    N = b.shape[-2]
+    if b.shape[-1] != K:
+        raise ValueError('gemm_nt: inner dimensions differ')
+    a_b, b_b = int(a.dim() == 3 and batch > 1), int(b.dim() == 3 and batch > 1)
+    out = th.empty((batch, M, N) if (a.dim() == 3 or b.dim() == 3) else (M, N), dtype=th.float32, device=a.device)
+    ws = L.workspace(lib.dg_gemm_nt_workspace_bytes(M, N, K, batch, a_b or batch == 1, b_b or batch == 1), a.device)
+    if row_scale is not None:
+        row_scale = row_scale.reshape(-1).to(th.float32).contiguous()
+        if row_scale.numel() != batch * M:
+            raise ValueError('gemm_nt: row_scale must have batch*M elements')
+    L.check(lib.dg_gemm_nt_f32(L.ptr(a), K, M * K if a_b else 0, L.ptr(b), K, N * K if b_b else 0, L.ptr(out), N, M * N,
+                               M, N, K, batch, L.ptr(row_scale), int(precision), L.ptr(ws), ws.numel(), L.stream()),
+            'gemm_nt')
+    return out
+
+
+class ProjectFunction(th.autograd.Function):
+    """y[r] = x @ w[r] for the R relation weights at once (x [M,K] shared, w [R,K,N]) -> [R,M,N]."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return gemm_nt(x, w.transpose(1, 2))                    # B[r] = w[r]^T  [N,K], K-major
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        dy = dy.contiguous()
+        if ctx.needs_input_grad[0]:
+            # dx = sum_r dy[r] @ w[r]^T = [dy_0 | dy_1 | ..] @ [w_0 | w_1 | ..]^T : one GEMM with K' = R*N
+            R, M, N = dy.shape
+            dx = gemm_nt(dy.permute(1, 0, 2).reshape(M, R * N), w.permute(1, 0, 2).reshape(w.shape[1], R * N))
+        if ctx.needs_input_grad[1]:
+            # dw[r] = x^T @ dy[r]: A = x^T [K,M] shared, B[r] = dy[r]^T [N,M]; long K = M -> split-K inside
+            dw = gemm_nt(x.t(), dy.transpose(1, 2))
+        return dx, dw
+
+
+def project(x, w):
+    """x [M,K] @ w [R,K,N] -> [R,M,N]; tcgen05 3xTF32 for the large projections, cuBLAS below GEMM_MIN_MACS."""
+    if not x.is_cuda:
+        raise RuntimeError('dreamgnn_b200.project needs CUDA tensors (no CPU fallback)')
+    R, K, N = w.shape
+    macs = x.shape[0] * K * N * R
+    if gemm_backend() == 'tcgen05' and x.dtype == th.float32 and macs >= GEMM_MIN_MACS:
+        return ProjectFunction.apply(x, w)
+    return th.matmul(x.unsqueeze(0), w)

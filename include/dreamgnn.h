@@ -148,6 +148,18 @@ DG_API int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_
                        float* dz1, float* dw2, float* db2, float* dw3, float* db3,
                        void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
+/* ---- dense projections on the tcgen05 tensor cores -------------------------------------------------
+ * C[b] = diag(row_scale[b]) * A[b] * B[b]^T for b < batch; A [M,K] row-major (lda), B [N,K] row-major
+ * (ldb), C [M,N] row-major (ldc); batch strides in elements, stride 0 = operand shared by all batches.
+ * precision 0: error-compensated 3xTF32 (fp32-level accuracy, the 1e-5 parity path); 1: single TF32.
+ * Replaces the cuBLAS GEMMs behind th.matmul(att, basis) @ feat (layers.py:120-121, 220-221, 392),
+ * th.mm(input, weight) (layers.py:311) and their backward. row_scale may be NULL. */
+DG_API size_t dg_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, int a_batched, int b_batched);
+DG_API int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B, int64_t ldb,
+                          int64_t stride_b, float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N,
+                          int64_t K, int64_t batch, const float* row_scale, int precision, void* workspace,
+                          size_t workspace_bytes, dg_stream_t stream);
+
 /* ---- kNN similarity graphs (data_loader.py:278-344, utils.py:11-27) ------------------------- */
 /* Per row of a float64 similarity block [n_rows, n_cols] (leading dimension ld), the k largest
  * entries under the tie rule (value descending, column ascending); out_idx [n_rows,k] ascending.

@@ -306,3 +306,41 @@ def test_launch_counter_counts_kernels(dev):
     _lib.reset_launch_count()
     ops().exclusive_scan_i32(th.ones(10000, dtype=th.int32, device=dev))
     assert _lib.launch_count() == 3
+
+
+# ---- tcgen05 projection GEMM -----------------------------------------------------------------------
+@pytest.mark.parametrize('M,N,K,R', [(1, 1, 1, 1), (128, 128, 32, 1), (130, 70, 36, 1), (257, 129, 100, 3),
+                                    (1000, 344, 1024, 2), (344, 96, 20000, 2)])
+def test_gemm_nt_3xtf32(dev, M, N, K, R):
+    gen = th.Generator().manual_seed(M + N + K)
+    a = th.randn(M, K, generator=gen)
+    b = th.randn(R, N, K, generator=gen) if R > 1 else th.randn(N, K, generator=gen)
+    rs = th.rand(R * M, generator=gen)
+    ref = (a.double() @ b.double().transpose(-1, -2)) * rs.double().view(R, M, 1).squeeze(0) if R > 1 else \
+        (a.double() @ b.double().t()) * rs.double().view(M, 1)
+    got = ops().gemm_nt(a.to(dev), b.to(dev), row_scale=rs.to(dev), precision=0)
+    assert H.rel_err(got.cpu(), ref) <= FP32_TOL
+    assert th.equal(got, ops().gemm_nt(a.to(dev), b.to(dev), row_scale=rs.to(dev), precision=0))    # deterministic split-K
+    tf32 = ops().gemm_nt(a.to(dev), b.to(dev), row_scale=rs.to(dev), precision=1)
+    assert H.rel_err(tf32.cpu(), ref) <= 2e-3
+
+
+def test_project_autograd_on_tensor_cores(dev):
+    o = ops()
+    gen = th.Generator().manual_seed(3)
+    x = th.randn(700, 96, generator=gen)
+    w = th.randn(2, 96, 40, generator=gen)
+    gout = th.randn(2, 700, 40, generator=gen)
+    old = o.GEMM_MIN_MACS
+    o.GEMM_MIN_MACS = 0
+    try:
+        xg, wg = x.to(dev).requires_grad_(True), w.to(dev).requires_grad_(True)
+        y = o.project(xg, wg)
+        y.backward(gout.to(dev))
+    finally:
+        o.GEMM_MIN_MACS = old
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = th.matmul(xr.unsqueeze(0), wr)
+    yr.backward(gout.double())
+    assert H.rel_err(y.detach().cpu(), yr.detach()) <= FP32_TOL
+    assert H.rel_err(xg.grad.cpu(), xr.grad) <= FP32_TOL and H.rel_err(wg.grad.cpu(), wr.grad) <= FP32_TOL

@@ -276,3 +276,26 @@ def test_training_matches_oracle_without_randomness(case, dev):
     sd = net.state_dict()
     for k, v in P.items():
         assert H.rel_err(sd[k].cpu(), v.detach()) <= 1e-4, k
+
+
+def test_net_parity_with_tensor_core_projections(case, dev):
+    """Same golden parity with every projection forced through the tcgen05 3xTF32 GEMM."""
+    from dreamgnn_b200 import ops
+    from dreamgnn_b200.utils import common_loss
+    name, g, built, knn = case
+    old = ops.GEMM_MIN_MACS
+    ops.GEMM_MIN_MACS = 0
+    try:
+        net = _net(g, name, dev).train()
+        out = net(*_inputs(g, built, knn, dev))
+        labels = th.tensor(g['train.labels']).to(dev)
+        loss = th.nn.BCEWithLogitsLoss()(out[0].squeeze(-1), labels) + 0.001 * (
+            common_loss(out[1], out[2]) + common_loss(out[3], out[4]))
+        loss.backward()
+    finally:
+        ops.GEMM_MIN_MACS = old
+    for nm, t in zip(('pred', 'drug_out', 'drug_sim_out', 'dis_out', 'dis_sim_out'), out):
+        assert H.rel_err(t.detach().cpu(), g['fwd.' + nm]) <= FP32_TOL, nm
+    for k, p in net.named_parameters():
+        if bool(g['hasgrad.' + k]):
+            assert H.rel_err(p.grad.cpu(), g['grad.' + k]) <= FP32_TOL, k
