@@ -132,17 +132,32 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     spec = synthetic.scaled(args.workload, args.scale)
-    th.manual_seed(1234 + rank)
-    w = synthetic.make_workload(spec, dev, seed=1234 + rank)            # each rank: its own fold-replica
-    state = synthetic.train_state(w, dev)
+    rows = args.parallel == 'rows' and world > 1
+    seed = 1234 if rows else 1234 + rank                              # rows: one graph, identical on every rank
+    th.manual_seed(seed)
+    w = synthetic.make_workload(spec, dev, seed=seed)                  # folds: each rank its own fold-replica
     margs = synthetic.model_args(w)
     model = Net(margs).to(dev)
     opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5)
-    loss_fn = th.nn.BCEWithLogitsLoss()
-    aug_methods = ['edge_dropout', 'feature_noise']
-    aug_params = aug_params_from_args(argparse.Namespace())
-    closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
-    step = lambda: train_iteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
+    if rows:
+        from dreamgnn_b200 import dist as D
+        part = D.Partition({'drug': spec['n_drug'], 'disease': spec['n_dis']})
+        knn = {k: w[k] for k in ('drug_graph', 'disease_graph', 'drug_feature_graph', 'disease_feature_graph')}
+        state = D.PartitionedState(part, w['pairs'], w['labels'], knn, w['drug_feat'], w['dis_feat'],
+                                   w['drug_sim_feat'], w['dis_sim_feat'], dev)
+        state.labels = state.dec.labels
+        n_pairs_total = state.dec.n_global
+        th.manual_seed(4321 + rank)                                    # per-rank dropout / noise streams
+        step = lambda: D.train_iteration_partitioned(model, opt, state)
+    else:
+        state = synthetic.train_state(w, dev)
+        n_pairs_total = state.labels.numel()
+        loss_fn = th.nn.BCEWithLogitsLoss()
+        aug_methods = ['edge_dropout', 'feature_noise']
+        aug_params = aug_params_from_args(argparse.Namespace())
+        closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
+        step = lambda: train_iteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
+    del w
 
     def barrier():
         if world > 1:
@@ -205,6 +220,8 @@ def run_b200(args):
             setattr(state, k, v.to(dev, non_blocking=True))
         if sim_is_feat:
             state.drug_sim_feat, state.dis_sim_feat = state.drug_feat, state.dis_feat
+        if rows:
+            state.dec.labels = state.labels
         loss_host = float(step().item())                                  # D2H read of the step's result
     e1.record()
     barrier()
@@ -216,8 +233,14 @@ def run_b200(args):
     # ---- metric ---------------------------------------------------------------------------------
     agg_edges = sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / args.steps
     it_s = args.steps / (ms_max / 1e3)
-    value = world * agg_edges * it_s / 1e9
-    e2e_value = world * agg_edges * (args.steps / (ms_e2e / 1e3)) / 1e9
+    if rows:                                                          # one job: edges are summed over ranks
+        t = th.tensor([agg_edges], device=dev, dtype=th.float64)
+        dist.all_reduce(t)
+        agg_edges = float(t.item())
+        value, e2e_value = agg_edges * it_s / 1e9, agg_edges * (args.steps / (ms_e2e / 1e3)) / 1e9
+    else:                                                             # N independent fold-replicas
+        value = world * agg_edges * it_s / 1e9
+        e2e_value = world * agg_edges * (args.steps / (ms_e2e / 1e3)) / 1e9
 
     # ---- roofline of the dominant kernel (largest total device time among the logged SpMM classes) --
     classes = {}
@@ -255,18 +278,20 @@ def run_b200(args):
 
     out = {'metric': 'aggregated_edges_per_sec', 'value': round(value, 4), 'unit': 'GE/s', 'n_gpus': world,
            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_max / args.steps, 3),
-           'iters_per_sec': round(world * it_s, 4), 'higher_is_better': True, 'scaling': 'weak',
+           'iters_per_sec': round((1 if rows else world) * it_s, 4), 'higher_is_better': True,
+           'scaling': 'strong' if rows else 'weak',
            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
            'config': {'workload': '%s: %d drugs x %d diseases, %d scored pairs, %d-/%d-dim features, k=%d, '
                                   'GCMC+FGCN 3 layers, 128 units, one fold per GPU'
-                                  % (args.workload, spec['n_drug'], spec['n_dis'], state.labels.numel(),
+                                  % (args.workload, spec['n_drug'], spec['n_dis'], n_pairs_total,
                                      spec['f_drug'], spec['f_dis'], spec['k']),
                       'step': 'augmentation + forward + loss + backward + clip + Adam (train.py:250-300)',
                       'aggregated_edges_per_step': int(agg_edges), 'scale': args.scale,
                       'l2': 'inputs larger than L2 (gathered operand %.0f MB, indices %.0f MB per SpMM)'
                             % (top['bmin'] / top['n'] / 1e6, top['nnz'] / top['n'] * 4 / 1e6)
                             if top['bmin'] / top['n'] > 126e6 else 'working set fits L2; no flush between steps',
-                      'parallelism': 'fold-replica per GPU, no collective' if world > 1 else 'single GPU',
+                      'parallelism': ('1-D row partition, NCCL all-gather of node rows per aggregation' if rows else
+                                      'fold-replica per GPU, no collective') if world > 1 else 'single GPU',
                       'common_loss': 'N x N (reference form)' if spec['kind'] == 'dense' else
                                      'Gram-matrix form of the same value (N x N does not fit at this shape)',
                       'fgcn_input': 'N x N similarity (reference)' if spec['kind'] == 'dense' else
@@ -416,10 +441,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='syn20m', choices=['syn20m', 'lrssl', 'gdataset', 'cdataset'])
+    ap.add_argument('--workload', default='syn20m', choices=['syn20m', 'syn400m', 'lrssl', 'gdataset', 'cdataset'])
     ap.add_argument('--scale', type=float, default=1.0, help='proportional shrink of the workload (tests)')
     ap.add_argument('--cpu-scale', type=float, default=0.0, help='scale of the CPU sample (default: scale/40 for syn*)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parallel', default='folds', choices=['folds', 'rows'],
+                    help='N>1: independent fold-replicas (weak scaling, default) or one row-partitioned graph (strong)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

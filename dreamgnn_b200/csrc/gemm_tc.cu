@@ -80,7 +80,7 @@ struct GemmParams {
   float* partial;          // [batch*splits, M, N] when splits > 1
   const float* row_scale;  // nullable, [batch * M]
   int64_t ldc, stride_c;
-  int M, N, nkb, kb_per_split, splits, a_batched, b_batched, vec_ok;
+  int M, N, nkb, kb_per_split, splits, a_batched, b_batched, vec_ok, n_tiles;
 };
 
 template <bool kSplit3>
@@ -98,8 +98,12 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
-  const int batch = blockIdx.z / p.splits, split = blockIdx.z - batch * p.splits;
+  // grid.x walks (n tile, batch) fastest so the CTAs that share one A row-panel are co-resident and the
+  // panel is fetched from HBM once (measured before: A re-read ~6x, kernel 65 % DRAM-bound)
+  const int batch = blockIdx.x / p.n_tiles;
+  const int m0 = blockIdx.y * kBM, n0 = (blockIdx.x - batch * p.n_tiles) * kBN;
+  const int split = blockIdx.z;
+  const int tile_z = batch * p.splits + split;                 // slot in the split-K partial buffer
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(p.nkb, kb0 + p.kb_per_split);
   const int n_iter = kb1 - kb0;
@@ -183,7 +187,7 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     float* out;
     int64_t ld;
     if (p.splits > 1) {
-      out = p.partial + (static_cast<int64_t>(blockIdx.z) * p.M + row) * p.N;
+      out = p.partial + (static_cast<int64_t>(tile_z) * p.M + row) * p.N;
       ld = p.N;
     } else {
       out = p.C + batch * p.stride_c + static_cast<int64_t>(row) * p.ldc;
@@ -359,7 +363,7 @@ int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B
   cudaStream_t st = as_stream(stream);
   const int a_batched = stride_a != 0 || batch == 1, b_batched = stride_b != 0 || batch == 1;
   GemmPlan g = plan_gemm(M, N, K, batch, a_batched, b_batched);
-  DG_REQUIRE((N + kBN - 1) / kBN <= 65535 && batch * g.splits <= 65535, "grid too large");
+  DG_REQUIRE((M + kBM - 1) / kBM <= 65535 && g.splits <= 65535, "grid too large");
   const bool split3 = precision == 0;
   Workspace w(workspace, workspace_bytes);
   float* a_hi = w.take<float>(g.a_elems);
@@ -391,8 +395,9 @@ int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B
   p.a_batched = (a_batched && batch > 1) ? 1 : 0; p.b_batched = (b_batched && batch > 1) ? 1 : 0;
   p.vec_ok = (g.splits > 1) ? (N % 4 == 0)
                             : ((ldc % 4 == 0) && (stride_c % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0));
-  const dim3 grid(static_cast<unsigned>((M + kBM - 1) / kBM), static_cast<unsigned>((N + kBN - 1) / kBN),
-                  static_cast<unsigned>(batch * g.splits));
+  p.n_tiles = static_cast<int>((N + kBN - 1) / kBN);
+  const dim3 grid(static_cast<unsigned>(p.n_tiles * batch), static_cast<unsigned>((M + kBM - 1) / kBM),
+                  static_cast<unsigned>(g.splits));
   const size_t smem = (split3 ? 3 * 4 : 6 * 2) * kTileBytes + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
   if (split3) {
     static bool attr = false;

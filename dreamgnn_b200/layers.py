@@ -199,17 +199,22 @@ class GCMCLayer(nn.Module):
         for dst_type in seen:
             blk = graph.block(dst_type)
             x = feats[blk.src_type]
-            if x.size(0) != blk.n_src:
+            part = getattr(graph, 'partition', None)             # row-partitioned graph: x holds the owned rows
+            if part is None and x.size(0) != blk.n_src:
                 raise ValueError('%s features have %d rows for %d nodes' % (blk.src_type, x.size(0), blk.n_src))
             wstack = th.stack([_pad_cols(weights[c[1]], mult) for c in blk.etypes], dim=0)   # [R, in, Dp]
             h = ops.project(x, wstack)                               # [R, N_src, Dp]: all relations' messages
             dp = wstack.shape[2]
             cj = graph.nodes[blk.src_type].data['cj']
             scale = th.stack([_flat_f32(self.conv.mods[c[1]].dropout(cj)) for c in blk.etypes], dim=0).reshape(-1)
-            if MESSAGE_DTYPE != th.float32:
-                h = h.to(MESSAGE_DTYPE)
-            agg = ops.spmm(blk.csr, h.reshape(blk.num_rel * blk.n_src, dp), src_scale=scale,
-                           dst_scale=_flat_f32(graph.nodes[dst_type].data['ci']), tag='gcmc')
+            ci = _flat_f32(graph.nodes[dst_type].data['ci'])
+            if part is not None:
+                from . import dist as _dist
+                agg = _dist.gcmc_aggregate(scale, h, blk, ci)        # all-gather over NVLink + local SpMM
+            else:
+                if MESSAGE_DTYPE != th.float32:
+                    h = h.to(MESSAGE_DTYPE)
+                agg = ops.spmm(blk.csr, h.reshape(blk.num_rel * blk.n_src, dp), src_scale=scale, dst_scale=ci, tag='gcmc')
             out[dst_type] = agg[:, :D] if dp != D else agg
         drug = self.dropout(self.agg_act(out['drug']))
         dis = self.dropout(self.agg_act(out['disease']))
@@ -244,11 +249,15 @@ class GraphConvolution(nn.Module):
         if d % 4:
             support = _pad_cols(support, 4)
             bias = _pad_cols(bias, 4) if bias is not None else None
-        out = ops.spmm(adjacency_csr(adj), support, bias=bias, relu=relu, tag='fgcn')
+        if hasattr(adj, 'partition'):                            # owned rows of a row-partitioned kNN graph
+            from . import dist as _dist
+            out = ops.spmm(adj.csr, _dist.all_gather_rows(support), bias=bias, relu=relu, tag='fgcn')
+        else:
+            out = ops.spmm(adjacency_csr(adj), support, bias=bias, relu=relu, tag='fgcn')
         return out[:, :d] if out.shape[1] != d else out
 
     def forward(self, input, adj):
-        if adj.device != input.device:
+        if not hasattr(adj, 'partition') and adj.device != input.device:
             adj = adj.to(input.device)
         return self.aggregate(self.support(input), adj)
 
@@ -345,11 +354,15 @@ class MLPDecoder(nn.Module):
         self.lin3.reset_parameters()
 
     def forward(self, graph, drug_feat, dis_feat):
-        pairs = graph.pair_graph()
         n_in = drug_feat.shape[1]
         w1 = self.lin1.weight
         pd = F.linear(drug_feat, w1[:, :n_in], self.lin1.bias)     # drug half of lin1 (+ bias)
         ps = F.linear(dis_feat, w1[:, n_in:])                      # disease half
+        if hasattr(graph, 'partition'):                            # this rank's slice of the pairs; node rows gathered
+            from . import dist as _dist
+            pairs, pd, ps = graph.pairs, _dist.all_gather_rows(pd), _dist.all_gather_rows(ps)
+        else:
+            pairs = graph.pair_graph()
         seed = int(th.randint(0, 2 ** 62, (1,)).item()) if self.training and self.dropout.p > 0 else 0
         return ops.decoder_mlp(pd, ps, self.lin2.weight, self.lin2.bias, self.lin3.weight, self.lin3.bias, pairs,
                                p=self.dropout.p, seed=seed, training=self.training)

@@ -60,6 +60,18 @@ def sparse_workload(spec, device, seed=1234, pos_rate=0.01, sim_dim=64):
     emb_d = th.randn(n_d, sim_dim, generator=gen, device=device, dtype=th.float64)
     emb_s = th.randn(n_s, sim_dim, generator=gen, device=device, dtype=th.float64)
     k = spec['k']
+    if max(n_d, n_s) > 250_000:
+        # exact cosine kNN is an N^2 fp64 GEMM (2 PFLOP at 1M nodes): the 400M-edge shape uses k distinct
+        # pseudo-random neighbours per node instead (same degree structure, same adjacency pipeline)
+        def rand_knn(n):
+            step = th.randint(1, max(n // (k + 1), 2), (n, k), generator=gen, device=device)
+            nbr = (th.arange(n, device=device).unsqueeze(1) + th.cumsum(step, 1)) % n
+            return GB.knn_graph_from_topk(th.sort(nbr, dim=1).values.to(th.int32))
+        graphs = dict(drug_graph=rand_knn(n_d), disease_graph=rand_knn(n_s), drug_feature_graph=rand_knn(n_d),
+                      disease_feature_graph=rand_knn(n_s))
+        return dict(spec=spec, pairs=pairs, labels=labels, drug_feat=drug_feat, dis_feat=dis_feat,
+                    drug_sim_feat=drug_feat, dis_sim_feat=dis_feat, fdim_drug=spec['f_drug'], fdim_disease=spec['f_dis'],
+                    **graphs)
     graphs = dict(drug_graph=GB.create_feature_similarity_graph(emb_d, k, device),
                   disease_graph=GB.create_feature_similarity_graph(emb_s, k, device),
                   drug_feature_graph=GB.create_feature_similarity_graph(drug_feat.double(), k, device),
