@@ -9,6 +9,8 @@
 // sums over the decoder graph's CSR/CSC (spmm.cu) -- no atomics anywhere.
 //
 // fp32 SIMT FMA (the 1e-5 parity path): E x 8192 MAC forward, E x 16384 MAC backward.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace dg {
@@ -18,8 +20,8 @@ constexpr int H2 = DG_DEC_H2;   // 64
 constexpr int kDecThreads = 256;
 
 struct DropCfg {
-  uint32_t thresh;   // floor(p * 2^32); 0 disables
-  float scale;       // 1 / (1 - p)
+  uint32_t thresh;   // round(p * 65536) on 16-bit uniforms; 0 disables
+  float scale;       // 1 / (actual keep probability)
   uint64_t seed;
 };
 
@@ -27,9 +29,9 @@ static DropCfg make_drop(float p, uint64_t seed) {
   DropCfg c;
   if (p <= 0.f) { c.thresh = 0; c.scale = 1.f; }
   else {
-    double t = static_cast<double>(p) * 4294967296.0;
-    c.thresh = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
-    c.scale = 1.f / (1.f - p);
+    long t = lround(static_cast<double>(p) * 65536.0);
+    c.thresh = static_cast<uint32_t>(t < 1 ? 1 : (t > 65535 ? 65535 : t));
+    c.scale = static_cast<float>(65536.0 / (65536.0 - c.thresh));     // unbiased for the quantised keep rate
   }
   c.seed = seed;
   return c;
@@ -67,10 +69,12 @@ __device__ __forceinline__ void gather_z1_tile(const int* __restrict__ src, cons
     for (int u = 0; u < U; ++u) {
       const int p = w * kPer + i0 + u;
       float z[4] = {a[u].x + b[u].x, a[u].y + b[u].y, a[u].z + b[u].z, a[u].w + b[u].w};
+      DropBits bits;
+      if (drop.thresh) bits = dropout_bits(drop.seed, static_cast<uint32_t>(e[u]), lane);      // units 4*lane .. +3
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float v = fmaxf(z[q], 0.f);
-        if (drop.thresh) v = dropout_keep(drop.seed, static_cast<uint64_t>(e[u]), lane * 4 + q, drop.thresh) ? v * drop.scale : 0.f;
+        if (drop.thresh) v = dropout_keep16(bits, q, drop.thresh) ? v * drop.scale : 0.f;
         z[q] = v;
       }
       *reinterpret_cast<float4*>(Z + p * H1 + lane * 4) = make_float4(z[0], z[1], z[2], z[3]);
@@ -136,10 +140,12 @@ decoder_fwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int
     for (int i = 0; i < 8; ++i) {
       const int64_t e = base + p0 + i;
       float z2[4] = {acc[i][0] + bias2.x, acc[i][1] + bias2.y, acc[i][2] + bias2.z, acc[i][3] + bias2.w};
+      DropBits bits;
+      if (drop.thresh) bits = dropout_bits(drop.seed, static_cast<uint32_t>(e), H1 / 4 + tj);   // units j0 .. j0+3
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float v = fmaxf(z2[q], 0.f);
-        if (drop.thresh) v = dropout_keep(drop.seed, static_cast<uint64_t>(e), H1 + j0 + q, drop.thresh) ? v * drop.scale : 0.f;
+        if (drop.thresh) v = dropout_keep16(bits, q, drop.thresh) ? v * drop.scale : 0.f;
         z2[q] = v;
       }
       if (z2_save && e < n_pairs) *reinterpret_cast<float4*>(z2_save + e * H2 + j0) = make_float4(z2[0], z2[1], z2[2], z2[3]);
