@@ -181,7 +181,12 @@ def run_b200(args):
         th.cuda.profiler.start()
     e0.record()
     marks, host_ms = [], []
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        # bounded run-ahead: the host may be at most one full step ahead of the device. Letting it fill the
+        # driver's launch queue made it block inside cudaLaunchKernel and (measured) stall the GPU for
+        # 50-200 ms at random; an event wait on step i-2 costs nothing and keeps the queue from saturating.
+        if i >= 2:
+            marks[i - 2].synchronize()
         t_h = time.perf_counter()
         loss = step()
         host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))

@@ -3,10 +3,12 @@
 //   * tcgen05.mma.kind::tf32 issued by one elected thread, accumulator in TMEM (128 lanes x 128 columns),
 //     operand tiles (128 rows x 32 fp32 = 128 B, SWIZZLE_128B, K-major) staged in shared memory by TMA,
 //     mbarrier full/empty ring between the TMA warp and the MMA warp, tcgen05.ld epilogue by 4 warps.
-//   * fp32 accuracy from error-compensated TF32 ("3xTF32"): every operand is split once into
-//     hi = rna_tf32(x) and lo = x - hi (exact), and D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulates in the
-//     same TMEM tile; the dropped lo*lo term is ~2^-22 relative. One stage carries the four tiles of a
-//     k-block so A_hi / B_hi are fetched once for two of the three products.
+//   * fp32 accuracy from error-compensated TF32 ("3xTF32"): D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulates
+//     in the same TMEM tile, with hi = rna_tf32(x) and lo = x - hi (exact); the dropped lo*lo term is ~2^-22
+//     relative. The split happens INSIDE the kernel: TMA lands the raw fp32 tile, which the tensor core
+//     reads as hi (tf32 = top 19 bits, i.e. truncation); eight warps write lo = x - trunc(x) next to it at the
+//     same swizzled position, fence the generic-proxy writes for the async proxy and hand the stage to the
+//     MMA warp -- operands are read from HBM once and no hi/lo copies are materialised.
 //   * long-K / small-output shapes (the weight-gradient GEMMs, K = number of nodes) are split along K into
 //     per-CTA partial tiles that a second kernel sums in a fixed order (deterministic, no atomics).
 //
@@ -21,7 +23,7 @@ namespace dg {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;            // tile; 32 fp32 = one 128-byte swizzle row
 constexpr int kTileBytes = kBM * kBK * 4;                // 16 KB per operand tile
-constexpr int kGemmThreads = 192;                        // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
+constexpr int kGemmThreads = 320;                        // warp 0 TMA, 1 MMA + TMEM, 2..5 epilogue, 6..9 hi/lo transform
 constexpr int kTmemCols = 128;
 constexpr uint32_t kSpinLimit = 1u << 22;                // watchdog: trap instead of hanging the GPU
 
@@ -85,8 +87,7 @@ struct GemmParams {
 
 template <bool kSplit3>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   constexpr int kTiles = kSplit3 ? 4 : 2;                        // tiles per stage
   constexpr int kStageBytes = kTiles * kTileBytes;
@@ -94,8 +95,9 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the dynamic window is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);     // full[kStages], empty[kStages], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  // barriers: full[kStages] (TMA landed), empty[kStages] (MMAs retired), ready[kStages] (hi/lo written), tmem_full
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // grid.x walks (n tile, batch) fastest so the CTAs that share one A row-panel are co-resident and the
@@ -108,11 +110,13 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const int kb1 = min(p.nkb, kb0 + p.kb_per_split);
   const int n_iter = kb1 - kb0;
 
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), tfull = smem_u32(bars + 2 * kStages);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), ready0 = smem_u32(bars + 2 * kStages),
+                 tfull = smem_u32(bars + 3 * kStages);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
+      mbar_init(ready0 + 8 * s, 8);                              // one arrival per transform warp (warps 2..9)
     }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,16 +139,10 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         mbar_wait(empty0 + 8 * s, (round & 1) ^ 1);
         const uint32_t dst = smem_u32(smem + s * kStageBytes);
         const uint32_t bar = full0 + 8 * s;
-        mbar_expect_tx(bar, kStageBytes);
+        mbar_expect_tx(bar, 2 * kTileBytes);
         const int k = (kb0 + it) * kBK;
-        tma_load_3d(dst, &tmA_hi, bar, k, m0, za);
-        if (kSplit3) {
-          tma_load_3d(dst + kTileBytes, &tmA_lo, bar, k, m0, za);
-          tma_load_3d(dst + 2 * kTileBytes, &tmB_hi, bar, k, n0, zb);
-          tma_load_3d(dst + 3 * kTileBytes, &tmB_lo, bar, k, n0, zb);
-        } else {
-          tma_load_3d(dst + kTileBytes, &tmB_hi, bar, k, n0, zb);
-        }
+        tma_load_3d(dst, &tmA, bar, k, m0, za);                                      // raw fp32 A tile -> becomes A_hi
+        tma_load_3d(dst + (kSplit3 ? 2 : 1) * kTileBytes, &tmB, bar, k, n0, zb);     // raw fp32 B tile -> becomes B_hi
       }
     }
   } else if (warp == 1) {
@@ -152,7 +150,7 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (lane == 0) {
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStages, round = it / kStages;
-        mbar_wait(full0 + 8 * s, round & 1);
+        mbar_wait((kSplit3 ? ready0 : full0) + 8 * s, round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t base = smem_u32(smem + s * kStageBytes);
         const uint64_t a_hi = smem_desc_sw128(base);
@@ -176,6 +174,33 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       umma_commit(tfull);                                       // accumulator complete
     }
   } else {
+    // ===== warps 2..9: hi/lo transform of every stage; warps 2..5 then run the epilogue =====
+    // The tensor core reads only the top 19 bits of an fp32 operand (tf32 = truncation), so the raw tile IS
+    // the hi operand: hi = x & 0xffffe000 implicitly, and lo = x - hi (exact) is written to the neighbouring
+    // tile at the same swizzled position. 32 KB read + 32 KB written per stage by 256 threads.
+    if (kSplit3) {
+      const int tt = threadIdx.x - 2 * 32;                      // 0..255
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % kStages, round = it / kStages;
+        mbar_wait(full0 + 8 * s, round & 1);
+        float4* st = reinterpret_cast<float4*>(smem + s * kStageBytes);
+#pragma unroll
+        for (int i = tt; i < 2 * (kTileBytes / 16); i += 256) {
+          // float4 index i: [0,1024) = A tile, [1024,2048) = B tile (which sits two tiles further)
+          const int idx = i < kTileBytes / 16 ? i : i + kTileBytes / 16;
+          const float4 x = st[idx];
+          st[idx + kTileBytes / 16] = make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u),
+                                                  x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u),
+                                                  x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u),
+                                                  x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready0 + 8 * s) : "memory");
+      }
+    }
+  }
+  if (warp >= 2 && warp < 6) {
     // ===== epilogue: TMEM -> registers -> global; warp w owns TMEM lanes 32*(w%4) .. +31 =====
     const int q = warp & 3;
     if (n_iter > 0) {
@@ -237,24 +262,18 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 }
 
-// hi = round-to-nearest tf32 (low 13 mantissa bits cleared), lo = x - hi (exact in fp32); packed [rows, kp]
-__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t ld, int64_t batch_stride, int rows, int k, int kp,
-                                  float* __restrict__ hi, float* __restrict__ lo) {
+// packing copy for operands TMA cannot address directly (row stride not a multiple of 16 bytes or a
+// misaligned base): packed [rows, kp] with zero padding
+__global__ void pack_rows_kernel(const float* __restrict__ x, int64_t ld, int64_t batch_stride, int rows, int k, int kp,
+                                 float* __restrict__ out) {
   const int64_t total = static_cast<int64_t>(rows) * kp;
-  const int64_t b = blockIdx.y;
-  const float* xb = x + b * batch_stride;
-  float* hb = hi + b * total;
-  float* lb = lo ? lo + b * total : nullptr;
+  const float* xb = x + blockIdx.y * batch_stride;
+  float* ob = out + blockIdx.y * total;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t r = i / kp;
     const int c = static_cast<int>(i - r * kp);
-    const float v = c < k ? xb[r * ld + c] : 0.f;
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-    const float hf = __uint_as_float(h);
-    hb[i] = hf;
-    if (lb) lb[i] = v - hf;
+    ob[i] = c < k ? xb[r * ld + c] : 0.f;
   }
 }
 
@@ -290,12 +309,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// packed [batch, rows, kp] fp32 tensor, box = 32 (k) x 128 (rows) x 1, 128-byte swizzle, OOB -> 0
-static int make_map(CUtensorMap* map, const float* base, int rows, int kp, int batch) {
+// [batch, rows, k] fp32 tensor with row stride `ld` and batch stride `bstride` (elements); box = 32 (k) x 128
+// (rows) x 1, 128-byte swizzle, out-of-bounds -> 0 (ragged M / N / K edges need no special casing)
+static int make_map(CUtensorMap* map, const float* base, int rows, int k, int64_t ld, int64_t bstride, int batch) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("gemm: cuTensorMapEncodeTiled not available from the driver"); return DG_ERR_UNSUPPORTED; }
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(kp), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(kp) * 4, static_cast<cuuint64_t>(kp) * 4 * rows};
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(batch > 1 ? bstride : ld * rows) * 4};
   cuuint32_t box[3] = {kBK, kBM, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
@@ -305,12 +325,16 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int kp, int b
   return DG_OK;
 }
 
+static bool tma_addressable(const float* p, int64_t ld, int64_t bstride, int64_t batch) {
+  return reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 4 == 0 && (batch <= 1 || bstride % 4 == 0);
+}
+
 struct GemmPlan {
-  int kp, nkb, splits, kb_per_split, a_copies, b_copies;
-  size_t a_elems, b_elems, partial_elems;
+  int kp, nkb, splits, kb_per_split;
+  size_t partial_elems;
 };
 
-static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int a_batched, int b_batched) {
+static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, int64_t batch) {
   GemmPlan g;
   g.kp = static_cast<int>((K + 3) / 4 * 4);
   g.nkb = static_cast<int>((K + kBK - 1) / kBK);
@@ -328,10 +352,6 @@ static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, int64_t batch, int a_
   if ((g.nkb + splits - 1) / splits > kMaxKbPerAccum) splits = (g.nkb + kMaxKbPerAccum - 1) / kMaxKbPerAccum;
   g.kb_per_split = (g.nkb + splits - 1) / splits;
   g.splits = (g.nkb + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
-  g.a_copies = a_batched ? static_cast<int>(batch) : 1;
-  g.b_copies = b_batched ? static_cast<int>(batch) : 1;
-  g.a_elems = static_cast<size_t>(g.a_copies) * M * g.kp;
-  g.b_elems = static_cast<size_t>(g.b_copies) * N * g.kp;
   g.partial_elems = g.splits > 1 ? static_cast<size_t>(batch) * g.splits * M * N : 0;
   return g;
 }
@@ -342,12 +362,10 @@ extern "C" {
 
 size_t dg_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, int a_batched, int b_batched) {
   using namespace dg;
-  GemmPlan g = plan_gemm(M, N, K, batch, a_batched, b_batched);
-  size_t b = 0;
-  b = ws_add(b, g.a_elems * 4);
-  b = ws_add(b, g.a_elems * 4);
-  b = ws_add(b, g.b_elems * 4);
-  b = ws_add(b, g.b_elems * 4);
+  GemmPlan g = plan_gemm(M, N, K, batch);
+  size_t b = 0;                                              // worst case: both operands need the packing copy
+  b = ws_add(b, static_cast<size_t>(a_batched ? batch : 1) * M * g.kp * 4);
+  b = ws_add(b, static_cast<size_t>(b_batched ? batch : 1) * N * g.kp * 4);
   b = ws_add(b, g.partial_elems * 4);
   return b;
 }
@@ -361,38 +379,37 @@ int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B
   DG_REQUIRE(lda >= K && ldb >= K && ldc >= N, "leading dimension too small");
   DG_REQUIRE(precision == 0 || precision == 1, "precision: 0 = 3xTF32 (fp32-accurate), 1 = single TF32");
   cudaStream_t st = as_stream(stream);
-  const int a_batched = stride_a != 0 || batch == 1, b_batched = stride_b != 0 || batch == 1;
-  GemmPlan g = plan_gemm(M, N, K, batch, a_batched, b_batched);
+  const int a_copies = (stride_a != 0 && batch > 1) ? static_cast<int>(batch) : 1;
+  const int b_copies = (stride_b != 0 && batch > 1) ? static_cast<int>(batch) : 1;
+  GemmPlan g = plan_gemm(M, N, K, batch);
   DG_REQUIRE((M + kBM - 1) / kBM <= 65535 && g.splits <= 65535, "grid too large");
   const bool split3 = precision == 0;
   Workspace w(workspace, workspace_bytes);
-  float* a_hi = w.take<float>(g.a_elems);
-  float* a_lo = w.take<float>(g.a_elems);
-  float* b_hi = w.take<float>(g.b_elems);
-  float* b_lo = w.take<float>(g.b_elems);
+  auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return static_cast<unsigned>(b > 148 * 16 ? 148 * 16 : (b ? b : 1)); };
+  int64_t ka = K, kb = K;
+  if (!tma_addressable(A, lda, stride_a, a_copies)) {
+    float* pa = w.take<float>(static_cast<size_t>(a_copies) * M * g.kp);
+    if (!pa) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
+    pack_rows_kernel<<<dim3(blocks(static_cast<size_t>(M) * g.kp), a_copies), 256, 0, st>>>(A, lda, stride_a, static_cast<int>(M), static_cast<int>(K), g.kp, pa);
+    DG_CHECK_LAUNCH("pack_rows(A)");
+    A = pa; lda = g.kp; stride_a = M * g.kp; ka = g.kp;
+  }
+  if (!tma_addressable(B, ldb, stride_b, b_copies)) {
+    float* pb = w.take<float>(static_cast<size_t>(b_copies) * N * g.kp);
+    if (!pb) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
+    pack_rows_kernel<<<dim3(blocks(static_cast<size_t>(N) * g.kp), b_copies), 256, 0, st>>>(B, ldb, stride_b, static_cast<int>(N), static_cast<int>(K), g.kp, pb);
+    DG_CHECK_LAUNCH("pack_rows(B)");
+    B = pb; ldb = g.kp; stride_b = N * g.kp; kb = g.kp;
+  }
   float* partial = g.partial_elems ? w.take<float>(g.partial_elems) : nullptr;
-  if (!a_hi || !a_lo || !b_hi || !b_lo || (g.partial_elems && !partial)) {
-    set_error("gemm: workspace too small");
-    return DG_ERR_WORKSPACE_TOO_SMALL;
-  }
-  {
-    auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return static_cast<unsigned>(b > 148 * 16 ? 148 * 16 : (b ? b : 1)); };
-    split_tf32_kernel<<<dim3(blocks(static_cast<size_t>(M) * g.kp), g.a_copies), 256, 0, st>>>(
-        A, lda, stride_a, static_cast<int>(M), static_cast<int>(K), g.kp, a_hi, split3 ? a_lo : nullptr);
-    DG_CHECK_LAUNCH("split_tf32(A)");
-    split_tf32_kernel<<<dim3(blocks(static_cast<size_t>(N) * g.kp), g.b_copies), 256, 0, st>>>(
-        B, ldb, stride_b, static_cast<int>(N), static_cast<int>(K), g.kp, b_hi, split3 ? b_lo : nullptr);
-    DG_CHECK_LAUNCH("split_tf32(B)");
-  }
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
-  DG_PROPAGATE(make_map(&mA_hi, a_hi, static_cast<int>(M), g.kp, g.a_copies));
-  DG_PROPAGATE(make_map(&mA_lo, split3 ? a_lo : a_hi, static_cast<int>(M), g.kp, g.a_copies));
-  DG_PROPAGATE(make_map(&mB_hi, b_hi, static_cast<int>(N), g.kp, g.b_copies));
-  DG_PROPAGATE(make_map(&mB_lo, split3 ? b_lo : b_hi, static_cast<int>(N), g.kp, g.b_copies));
+  if (g.partial_elems && !partial) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
+  CUtensorMap mA, mB;
+  DG_PROPAGATE(make_map(&mA, A, static_cast<int>(M), static_cast<int>(ka), lda, stride_a, a_copies));
+  DG_PROPAGATE(make_map(&mB, B, static_cast<int>(N), static_cast<int>(kb), ldb, stride_b, b_copies));
   GemmParams p;
   p.C = C; p.partial = partial; p.row_scale = row_scale; p.ldc = ldc; p.stride_c = stride_c;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.nkb = g.nkb; p.kb_per_split = g.kb_per_split; p.splits = g.splits;
-  p.a_batched = (a_batched && batch > 1) ? 1 : 0; p.b_batched = (b_batched && batch > 1) ? 1 : 0;
+  p.a_batched = a_copies > 1 ? 1 : 0; p.b_batched = b_copies > 1 ? 1 : 0;
   p.vec_ok = (g.splits > 1) ? (N % 4 == 0)
                             : ((ldc % 4 == 0) && (stride_c % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0));
   p.n_tiles = static_cast<int>((N + kBN - 1) / kBN);
@@ -402,17 +419,17 @@ int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B
   if (split3) {
     static bool attr = false;
     if (!attr) { DG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
-    gemm_nt_tf32_kernel<true><<<grid, kGemmThreads, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+    gemm_nt_tf32_kernel<true><<<grid, kGemmThreads, smem, st>>>(mA, mB, p);
   } else {
     static bool attr = false;
     if (!attr) { DG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
-    gemm_nt_tf32_kernel<false><<<grid, kGemmThreads, smem, st>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+    gemm_nt_tf32_kernel<false><<<grid, kGemmThreads, smem, st>>>(mA, mB, p);
   }
   DG_CHECK_LAUNCH("gemm_nt_tf32");
   if (g.splits > 1) {
     size_t per = static_cast<size_t>(M) * N;
-    unsigned blocks = static_cast<unsigned>((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
-    splitk_reduce_kernel<<<dim3(blocks, static_cast<unsigned>(batch)), 256, 0, st>>>(partial, g.splits, p.M, p.N, C, ldc, stride_c, row_scale);
+    unsigned nb = static_cast<unsigned>((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
+    splitk_reduce_kernel<<<dim3(nb, static_cast<unsigned>(batch)), 256, 0, st>>>(partial, g.splits, p.M, p.N, C, ldc, stride_c, row_scale);
     DG_CHECK_LAUNCH("splitk_reduce");
   }
   return DG_OK;
