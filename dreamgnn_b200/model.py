@@ -1,54 +1,57 @@
-"""Drop-in mirror of the reference's `model.py` `Net` (model.py:4-103): same `args` fields, same
-submodule / parameter names (checkpoints interchange), same forward signature and 5-tuple return."""
+"""`Net` -- drop-in for the reference's top-level module (model.py:4-103).
+
+Contract kept: `Net(args)` consumes the same `args` attributes, registers its children under the same
+names (`TGCN.<l>`, `FGCN`, `attention`, `decoder` -> identical state_dict keys), builds them in the same
+order (so a given torch seed yields identical initial weights), and `forward` takes the reference's eleven
+arguments and returns `(pred, drug_out, drug_sim_out, dis_out, dis_sim_out)`.
+"""
 import torch as th
 import torch.nn as nn
 
-from .layers import FGCN, Attention, GCMCLayer, MLPDecoder
+from . import layers as L
 from .utils import get_activation
+
+
+def _topology_layer(args, act, first):
+    """GCMC layer l: layer 0 maps the raw embeddings (src/dst widths, msg = gcn_agg_units // 3);
+    deeper layers are out_units -> out_units with `ini=False` (model.py:9-42)."""
+    n_out = args.gcn_out_units
+    if first:
+        dims, msg, extra = (args.src_in_units, args.dst_in_units), args.gcn_agg_units, {}
+    else:
+        stacked = args.gcn_agg_accum == 'stack'
+        dims, msg, extra = (n_out, n_out), n_out * (len(args.rating_vals) if stacked else 1), {'ini': False}
+    return L.GCMCLayer(args.rating_vals, dims[0], dims[1], msg, n_out, args.dropout, args.gcn_agg_accum,
+                       agg_act=act, share_user_item_param=args.share_param, device=args.device, **extra)
 
 
 class Net(nn.Module):
     def __init__(self, args):
         super().__init__()
-        self.layers = args.layers
+        for name in ('layers', 'gcn_agg_accum', 'rating_vals', 'device', 'gcn_agg_units', 'src_in_units'):
+            setattr(self, name, getattr(args, name))
         self._act = get_activation(args.model_activation)
-        self.TGCN = nn.ModuleList()
-        self.TGCN.append(GCMCLayer(args.rating_vals, args.src_in_units, args.dst_in_units, args.gcn_agg_units,
-                                   args.gcn_out_units, args.dropout, args.gcn_agg_accum, agg_act=self._act,
-                                   share_user_item_param=args.share_param, device=args.device))
-        self.gcn_agg_accum = args.gcn_agg_accum
-        self.rating_vals = args.rating_vals
-        self.device = args.device
-        self.gcn_agg_units = args.gcn_agg_units
-        self.src_in_units = args.src_in_units
-        for _ in range(1, args.layers):
-            if args.gcn_agg_accum == 'stack':
-                gcn_out_units = args.gcn_out_units * len(args.rating_vals)
-            else:
-                gcn_out_units = args.gcn_out_units
-            self.TGCN.append(GCMCLayer(args.rating_vals, args.gcn_out_units, args.gcn_out_units, gcn_out_units,
-                                       args.gcn_out_units, args.dropout, args.gcn_agg_accum, agg_act=self._act,
-                                       share_user_item_param=args.share_param, ini=False, device=args.device))
-        self.FGCN = FGCN(args.fdim_drug, args.fdim_disease, args.nhid1, args.nhid2, args.dropout)
-        self.attention = Attention(args.gcn_out_units, dropout_rate=args.attention_dropout)
-        self.decoder = MLPDecoder(in_units=args.gcn_out_units, dropout_rate=args.dropout)
+        self.TGCN = nn.ModuleList(_topology_layer(args, self._act, first=(l == 0)) for l in range(args.layers))
+        self.FGCN = L.FGCN(args.fdim_drug, args.fdim_disease, args.nhid1, args.nhid2, args.dropout)
+        self.attention = L.Attention(args.gcn_out_units, dropout_rate=args.attention_dropout)
+        self.decoder = L.MLPDecoder(in_units=args.gcn_out_units, dropout_rate=args.dropout)
+
+    def _topology_route(self, enc_graph, drug, dis, two_stage):
+        """Stacked GCMC layers with the 1/(l+1)-weighted sum of their outputs (model.py:67-76)."""
+        acc = None
+        for depth, layer in enumerate(self.TGCN, start=1):
+            drug, dis = layer(enc_graph, drug, dis, two_stage)
+            acc = (drug, dis) if acc is None else (acc[0] + drug / float(depth), acc[1] + dis / float(depth))
+        return acc
+
+    def _fuse(self, topo, feat):
+        """Shared two-view attention (model.py:93-97)."""
+        return self.attention(th.stack((topo, feat), dim=1))[0]
 
     def forward(self, enc_graph, dec_graph, drug_graph, drug_sim_feat, drug_feat, dis_graph, disease_sim_feat,
                 dis_feat, drug_feature_graph=None, disease_feature_graph=None, Two_Stage=False):
-        # topology route: layer-weighted sum o0 + o1/2 + o2/3 (model.py:67-76)
-        for i in range(self.layers):
-            drug_o, dis_o = self.TGCN[i](enc_graph, drug_feat, dis_feat, Two_Stage)
-            if i == 0:
-                drug_out, dis_out = drug_o, dis_o
-            else:
-                drug_out = drug_out + drug_o / float(i + 1)
-                dis_out = dis_out + dis_o / float(i + 1)
-            drug_feat, dis_feat = drug_o, dis_o
-        # feature route over the kNN similarity graphs (model.py:79-83)
+        drug_out, dis_out = self._topology_route(enc_graph, drug_feat, dis_feat, Two_Stage)
         drug_sim_out, dis_sim_out = self.FGCN(drug_graph, drug_sim_feat, dis_graph, disease_sim_feat,
                                               drug_feature_graph, disease_feature_graph)[:2]
-        # shared attention over the two views, drug first (model.py:93-97)
-        drug_feats, _ = self.attention(th.stack([drug_out, drug_sim_out], dim=1))
-        dis_feats, _ = self.attention(th.stack([dis_out, dis_sim_out], dim=1))
-        pred_ratings = self.decoder(dec_graph, drug_feats, dis_feats)
-        return pred_ratings, drug_out, drug_sim_out, dis_out, dis_sim_out
+        scores = self.decoder(dec_graph, self._fuse(drug_out, drug_sim_out), self._fuse(dis_out, dis_sim_out))
+        return scores, drug_out, drug_sim_out, dis_out, dis_sim_out
