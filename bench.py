@@ -131,6 +131,10 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
+    if args.cuda_graph:
+        # nothing may ever touch the legacy default stream: autograd binds each parameter's gradient
+        # accumulation to the stream of its first use, and the legacy stream cannot take part in a capture
+        th.cuda.set_stream(th.cuda.Stream(device=dev))
     if args.messages == 'bf16':
         from dreamgnn_b200 import layers as _layers
         _layers.MESSAGE_DTYPE = th.bfloat16
@@ -141,7 +145,7 @@ def run_b200(args):
     w = synthetic.make_workload(spec, dev, seed=seed)                  # folds: each rank its own fold-replica
     margs = synthetic.model_args(w)
     model = Net(margs).to(dev)
-    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5)
+    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5, capturable=args.cuda_graph)
     if rows:
         from dreamgnn_b200 import dist as D
         part = D.Partition({'drug': spec['n_drug'], 'disease': spec['n_dis']})
@@ -160,6 +164,20 @@ def run_b200(args):
         aug_params = aug_params_from_args(argparse.Namespace())
         closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
         step = lambda: train_iteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
+        eager_log, eager_launches = None, 0
+        if args.cuda_graph:
+            # kernels replayed from a graph are invisible to the Python-side launch log and counter: take both
+            # from one eager step of the identical iteration (same kernels, same shapes) before capturing
+            from dreamgnn_b200.graphed import GraphedIteration
+            for _ in range(2):
+                step()
+            th.cuda.synchronize()
+            ops.PROFILE = []
+            _lib.reset_launch_count()
+            step()
+            th.cuda.synchronize()
+            eager_log, eager_launches, ops.PROFILE = ops.PROFILE, _lib.launch_count(), None
+            step = GraphedIteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
     del w
 
     def barrier():
@@ -208,6 +226,8 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count()
     log, ops.PROFILE = ops.PROFILE, None
+    if args.cuda_graph and not rows:
+        log, launches = eager_log * args.steps, eager_launches * args.steps
     clocks = sampler.stop()
     t = th.tensor([ms], device=dev)
     if world > 1:
@@ -313,6 +333,7 @@ def run_b200(args):
                                      spec['f_drug'], spec['f_dis'], spec['k']),
                       'step': 'augmentation + forward + loss + backward + clip + Adam (train.py:250-300)',
                       'aggregated_edges_per_step': int(agg_edges), 'scale': args.scale,
+                      'launch': 'one CUDA-graph replay per step' if args.cuda_graph else 'eager launches',
                       'l2': 'inputs larger than L2 (gathered operand %.0f MB, indices %.0f MB per SpMM)'
                             % (top['bmin'] / top['n'] / 1e6, top['nnz'] / top['n'] * 4 / 1e6)
                             if top['bmin'] / top['n'] > 126e6 else 'working set fits L2; no flush between steps',
@@ -472,6 +493,8 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='proportional shrink of the workload (tests)')
     ap.add_argument('--cpu-scale', type=float, default=0.0, help='scale of the CPU sample (default: scale/40 for syn*)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cuda-graph', action='store_true',
+                    help='replay the whole training iteration from one captured CUDA graph (launch-bound small shapes)')
     ap.add_argument('--messages', default='f32', choices=['f32', 'bf16'],
                     help='storage of the gathered GCMC messages: f32 (1e-5 parity path, default) or bf16 (2e-2 path)')
     ap.add_argument('--parallel', default='folds', choices=['folds', 'rows'],

@@ -27,6 +27,14 @@ def num_keep_edges(num_edges, dropout_rate):
     return max(1, int(num_edges * (1 - dropout_rate)))
 
 
+def _randperm(n, device):
+    """th.randperm on the graph's device (augmentation.py:51, :117). Under CUDA-graph capture torch's small-n
+    path (n < 30000 is drawn on the CPU and copied) cannot be recorded, so a random-key argsort stands in."""
+    if n < 30000 and th.device(device).type == 'cuda' and th.cuda.is_current_stream_capturing():
+        return th.argsort(th.rand(n, device=device))
+    return th.randperm(n, device=device)
+
+
 def _sparse_from_csr(csr, shape, bwd=None):
     idx = th.stack([csr.rows().long(), csr.indices.long()])
     t = th.sparse_coo_tensor(idx, csr.vals, shape, device=csr.device, check_invariants=False)
@@ -47,7 +55,7 @@ class GraphAugmentation:
             n = graph.number_of_edges(c)
             if n == 0:
                 continue
-            perms[c] = (th.randperm(n, device=device), num_keep_edges(n, dropout_rate))
+            perms[c] = (_randperm(n, device), num_keep_edges(n, dropout_rate))
         return graph.edge_dropout(perms)
 
     @staticmethod
@@ -69,7 +77,7 @@ class GraphAugmentation:
             sparse_graph._dg_csr = base = nb
         n = base.nnz
         k = num_keep_edges(n, dropout_rate)
-        perm = th.randperm(n, device=sparse_graph.device)
+        perm = _randperm(n, sparse_graph.device)
         flags = ops.keep_flags(n, [(perm, k, 0)], base.device)
         return _sparse_from_csr(ops.csr_dropout(base, flags, k), sparse_graph.shape)
 

@@ -23,9 +23,10 @@ struct DropCfg {
   uint32_t thresh;   // round(p * 65536) on 16-bit uniforms; 0 disables
   float scale;       // 1 / (actual keep probability)
   uint64_t seed;
+  const uint64_t* seed_dev;   // when non-null the seed is read from device memory (CUDA-graph replays)
 };
 
-static DropCfg make_drop(float p, uint64_t seed) {
+static DropCfg make_drop(float p, uint64_t seed, const uint64_t* seed_dev) {
   DropCfg c;
   if (p <= 0.f) { c.thresh = 0; c.scale = 1.f; }
   else {
@@ -34,6 +35,7 @@ static DropCfg make_drop(float p, uint64_t seed) {
     c.scale = static_cast<float>(65536.0 / (65536.0 - c.thresh));     // unbiased for the quantised keep rate
   }
   c.seed = seed;
+  c.seed_dev = seed_dev;
   return c;
 }
 
@@ -93,6 +95,7 @@ decoder_fwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int
                    const float* __restrict__ pd, const float* __restrict__ ps, const float* __restrict__ w2,
                    const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
                    DropCfg drop, float* __restrict__ out, float* __restrict__ z2_save) {
+  if (drop.seed_dev) drop.seed = *drop.seed_dev;
   extern __shared__ __align__(16) float smem[];
   float* W2T = smem;               // [H1][H2]  (k-major so a thread reads its 4 units as one float4)
   float* Z = smem + H1 * H2;       // [kFwdTile][H1]
@@ -175,6 +178,7 @@ decoder_bwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int
                    const float* __restrict__ pd, const float* __restrict__ ps, const float* __restrict__ w2,
                    const float* __restrict__ w3, DropCfg drop, const float* __restrict__ z2,
                    const float* __restrict__ dout, float* __restrict__ dz1, float* __restrict__ partials) {
+  if (drop.seed_dev) drop.seed = *drop.seed_dev;
   extern __shared__ __align__(16) float smem[];
   float* W2S = smem;                          // [H2][H1] as stored
   float* Z = W2S + H2 * H1;                   // [kBwdTile][H1]
@@ -336,7 +340,7 @@ extern "C" {
 
 int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, const float* pd, const float* ps,
                        const float* w2, const float* b2, const float* w3, const float* b3, float dropout_p,
-                       uint64_t seed, float* out, float* z2_save, dg_stream_t stream) {
+                       uint64_t seed, const uint64_t* seed_dev, float* out, float* z2_save, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(n_pairs >= 0, "n_pairs < 0");
   DG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p must be in [0,1)");
@@ -348,7 +352,7 @@ int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, 
   }
   const int64_t n_tiles = (n_pairs + kFwdTile - 1) / kFwdTile;
   decoder_fwd_kernel<<<decoder_grid(n_tiles), kDecThreads, kFwdSmem, as_stream(stream)>>>(
-      src, dst, n_pairs, pd, ps, w2, b2, w3, b3, make_drop(dropout_p, seed), out, z2_save);
+      src, dst, n_pairs, pd, ps, w2, b2, w3, b3, make_drop(dropout_p, seed, seed_dev), out, z2_save);
   DG_CHECK_LAUNCH("decoder_fwd");
   return DG_OK;
 }
@@ -359,7 +363,7 @@ size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs) {
 }
 
 int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, const float* pd, const float* ps,
-                       const float* w2, const float* w3, float dropout_p, uint64_t seed, const float* z2,
+                       const float* w2, const float* w3, float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* z2,
                        const float* dout, float* dz1, float* dw2, float* db2, float* dw3, float* db3,
                        void* workspace, size_t workspace_bytes, dg_stream_t stream) {
   using namespace dg;
@@ -376,7 +380,7 @@ int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, 
   const int64_t n_tiles = (n_pairs + kBwdTile - 1) / kBwdTile;
   const int grid = decoder_grid(n_tiles);
   decoder_bwd_kernel<<<grid, kDecThreads, kBwdSmem, as_stream(stream)>>>(
-      src, dst, n_pairs, pd, ps, w2, w3, make_drop(dropout_p, seed), z2, dout, dz1, partials);
+      src, dst, n_pairs, pd, ps, w2, w3, make_drop(dropout_p, seed, seed_dev), z2, dout, dz1, partials);
   DG_CHECK_LAUNCH("decoder_bwd");
   constexpr int kOut = H2 * H1 + 2 * H2 + 1;
   decoder_reduce_partials<<<(kOut + 255) / 256, 256, 0, as_stream(stream)>>>(partials, grid, dw2, db2, dw3, db3);

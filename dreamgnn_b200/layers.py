@@ -363,7 +363,10 @@ class MLPDecoder(nn.Module):
             pairs, pd, ps = graph.pairs, _dist.all_gather_rows(pd), _dist.all_gather_rows(ps)
         else:
             pairs = graph.pair_graph()
-        seed = int(th.randint(0, 2 ** 62, (1,)).item()) if self.training and self.dropout.p > 0 else 0
+        seed = 0
+        if self.training and self.dropout.p > 0:
+            # drawn on device (no host sync, and a captured CUDA graph gets a fresh seed on every replay)
+            seed = th.randint(0, 2 ** 62, (1,), device=pd.device, dtype=th.int64)
         return ops.decoder_mlp(pd, ps, self.lin2.weight, self.lin2.bias, self.lin3.weight, self.lin3.bias, pairs,
                                p=self.dropout.p, seed=seed, training=self.training)
 

@@ -280,13 +280,16 @@ class DecoderFunction(th.autograd.Function):
         if pd.shape[0] != pairs.n_src or ps.shape[0] != pairs.n_dst:
             raise ValueError('decoder: node counts do not match the pair graph')
         e = pairs.n_pairs
+        # `seed` is a Python int, or a 1-element int64 CUDA tensor (read on device: CUDA-graph friendly)
+        seed_dev = seed if isinstance(seed, th.Tensor) else None
+        seed_val = 0 if seed_dev is not None else int(seed)
         out = th.empty(e, dtype=th.float32, device=pd.device)
         z2 = th.empty((e, DEC_H2), dtype=th.float32, device=pd.device) if save else None
         L.check(lib.dg_decoder_fwd_f32(L.ptr(pairs.src), L.ptr(pairs.dst), e, L.ptr(pd, th.float32, 'pd'),
                                        L.ptr(ps, th.float32, 'ps'), L.ptr(w2, th.float32), L.ptr(b2, th.float32),
-                                       L.ptr(w3, th.float32), L.ptr(b3, th.float32), float(p), int(seed), L.ptr(out),
+                                       L.ptr(w3, th.float32), L.ptr(b3, th.float32), float(p), seed_val, L.ptr(seed_dev), L.ptr(out),
                                        L.ptr(z2), L.stream()), 'decoder_fwd')
-        ctx.pairs, ctx.p, ctx.seed = pairs, float(p), int(seed)
+        ctx.pairs, ctx.p, ctx.seed, ctx.seed_dev = pairs, float(p), seed_val, seed_dev
         ctx.save_for_backward(pd, ps, w2, w3, z2)
         return out.unsqueeze(1)
 
@@ -307,7 +310,7 @@ class DecoderFunction(th.autograd.Function):
         db3 = th.empty(1, dtype=th.float32, device=dev)
         ws = L.workspace(lib.dg_decoder_bwd_workspace_bytes(e), dev)
         L.check(lib.dg_decoder_bwd_f32(L.ptr(pairs.src), L.ptr(pairs.dst), e, L.ptr(pd), L.ptr(ps), L.ptr(w2),
-                                       L.ptr(w3), ctx.p, ctx.seed, L.ptr(z2), L.ptr(dout, th.float32, 'dout'),
+                                       L.ptr(w3), ctx.p, ctx.seed, L.ptr(ctx.seed_dev), L.ptr(z2), L.ptr(dout, th.float32, 'dout'),
                                        L.ptr(dz1), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3), L.ptr(ws),
                                        ws.numel(), L.stream()), 'decoder_bwd')
         # scatter of dz1 into node gradients = two segment sums in fixed order (no atomics)

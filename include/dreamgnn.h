@@ -128,13 +128,15 @@ DG_API int dg_spmm_csr_bf16(const int32_t* indptr, const int32_t* indices, const
  * the kernel gathers them per pair (SDDMM-style) instead of materialising the [E,256] concat:
  *   z1 = drop(relu(pd[src]+ps[dst]));  z2 = drop(relu(W2 z1 + b2));  out = w3.z2 + b3
  * Hidden widths 128 / 64 are fixed by the reference (layers.py:349-351). Dropout uses a counter
- * based generator keyed by (seed, pair, unit); p == 0 disables it (eval mode). */
+ * based generator keyed by (seed, pair, unit); p == 0 disables it (eval mode). When `seed_dev` is non-NULL
+ * the seed is read from that device word instead of `seed`, so a captured CUDA graph draws a fresh mask
+ * on every replay. */
 #define DG_DEC_H1 128
 #define DG_DEC_H2 64
 DG_API int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
                        const float* pd, const float* ps, const float* w2, const float* b2,
                        const float* w3, const float* b3, float dropout_p, uint64_t seed,
-                       float* out, float* z2_save /* nullable: [n_pairs,64] kept for backward */,
+                       const uint64_t* seed_dev, float* out, float* z2_save /* nullable: [n_pairs,64] kept for backward */,
                        dg_stream_t stream);
 /* Backward: regenerates z1 (same dropout mask), reads the z2 the forward saved, writes
  * dz1 [n_pairs,128] = d loss / d (pd[src]+ps[dst]) and the parameter gradients dw2 [64,128], db2 [64],
@@ -144,7 +146,8 @@ DG_API int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_
 DG_API size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs);
 DG_API int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
                        const float* pd, const float* ps, const float* w2, const float* w3,
-                       float dropout_p, uint64_t seed, const float* z2, const float* dout,
+                       float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* z2,
+                       const float* dout,
                        float* dz1, float* dw2, float* db2, float* dw3, float* db3,
                        void* workspace, size_t workspace_bytes, dg_stream_t stream);
 

@@ -267,7 +267,7 @@ def test_decoder_dropout_is_consistent_between_forward_and_backward(dev):
     zs, w_ones, b_zero, w3_ones, b3_zero = (th.zeros_like(ps), th.ones(64, 128, device=dev), th.zeros(64, device=dev),
                                             th.ones(64, device=dev), th.zeros(1, device=dev))
     o.L.check(lib.dg_decoder_fwd_f32(o.L.ptr(pairs.src), o.L.ptr(pairs.dst), e, o.L.ptr(big), o.L.ptr(zs), o.L.ptr(w_ones),
-                                     o.L.ptr(b_zero), o.L.ptr(w3_ones), o.L.ptr(b3_zero), p, 42, o.L.ptr(outp), o.L.ptr(z2),
+                                     o.L.ptr(b_zero), o.L.ptr(w3_ones), o.L.ptr(b3_zero), p, 42, None, o.L.ptr(outp), o.L.ptr(z2),
                                      o.L.stream()), 'decoder_fwd')
     th.cuda.synchronize()
     kept2 = float((z2 > 0).float().mean())
