@@ -78,3 +78,43 @@ def _worker(rank, world, port):
 @pytest.mark.skipif(th.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
 def test_row_partitioned_equals_single_gpu():
     mp.spawn(_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _cv_worker(rank, world, port, root):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    os.chdir(root)
+    from dreamgnn_b200 import cv_shard
+    cv_shard.main(['--data_name', 'lrssl', '--train_max_iter', '5', '--train_valid_interval', '2', '--gcn_agg_units', '105',
+                   '--gcn_out_units', '16', '--nhid1', '40', '--nhid2', '16', '--num_neighbor', '4', '--seeds', '77', '31415',
+                   '--folds', '3'])
+
+
+@pytest.mark.skipif(th.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_fold_sharded_cv_two_gpus():
+    """The fold/seed launcher end to end over NCCL: 2 seeds x 3 folds dealt to 2 GPUs, results gathered on rank 0
+    and written in the reference's CSV layout."""
+    import tempfile
+
+    import numpy as np
+    import scipy.io as sio
+
+    from tests import helpers as H
+    g = H.load_golden('tinyA')
+    root = tempfile.mkdtemp(prefix='dg_cv2_')
+    d = os.path.join(root, 'raw_data', 'drug_data', 'lrssl')
+    os.makedirs(d)
+    names = np.empty((60, 1), dtype=object)
+    for i in range(60):
+        names[i, 0] = np.array(['DB%05d' % i])
+    sio.savemat(os.path.join(d, 'lrssl.mat'), {'didr': g['mat.didr'], 'drug': g['mat.drug'], 'disease': g['mat.disease'],
+                                               'drug_embed': g['mat.drug_embed'], 'disease_embed': g['mat.disease_embed'],
+                                               'Wrname': names})
+    mp.spawn(_cv_worker, args=(2, _free_port(), root), nprocs=2, join=True)
+    summary = open(os.path.join(root, 'seed_experiments', 'summary_results.csv')).read().splitlines()
+    assert summary[0] == 'experiment,seed,avg_auroc,avg_aupr' and len(summary) == 4
+    rows = open(os.path.join(root, 'seed_experiments', 'seed_77', 'experiment_results.csv')).read().splitlines()
+    assert len(rows) == 5 and rows[-1].startswith('average,')
+    for r in rows[1:4]:
+        a, p = map(float, r.split(',')[1:])
+        assert 0.0 <= a <= 1.0 and 0.0 <= p <= 1.0
