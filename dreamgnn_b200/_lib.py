@@ -11,7 +11,7 @@ import torch as th
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'lib', 'libdreamgnn.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _P = c_void_p
 _SIGNATURES = {
@@ -32,9 +32,9 @@ _SIGNATURES = {
     'dg_csr_expand_rows': (c_int, [_P, c_int64, _P, _P]),
     'dg_spmm_csr_f32': (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int, _P]),
     'dg_spmm_csr_bf16': (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int, _P]),
-    'dg_decoder_fwd_f32': (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_float, c_uint64, _P, _P, _P, _P]),
+    'dg_decoder_fwd_f32': (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_float, c_uint64, _P, _P, _P, _P]),
     'dg_decoder_bwd_workspace_bytes': (c_size_t, [c_int64]),
-    'dg_decoder_bwd_f32': (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_float, c_uint64, _P, _P, _P, _P, _P, _P, _P, _P,
+    'dg_decoder_bwd_f32': (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_float, c_uint64, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _P, c_size_t, _P]),
     'dg_gemm_nt_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
     'dg_gemm_nt_f32': (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64,

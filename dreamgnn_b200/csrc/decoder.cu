@@ -10,34 +10,13 @@
 //
 // fp32 SIMT FMA (the 1e-5 parity path): E x 8192 MAC forward, E x 16384 MAC backward.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "decoder_common.cuh"
 
 namespace dg {
-
-constexpr int H1 = DG_DEC_H1;   // 128
-constexpr int H2 = DG_DEC_H2;   // 64
-constexpr int kDecThreads = 256;
-
-struct DropCfg {
-  uint32_t thresh;   // round(p * 65536) on 16-bit uniforms; 0 disables
-  float scale;       // 1 / (actual keep probability)
-  uint64_t seed;
-  const uint64_t* seed_dev;   // when non-null the seed is read from device memory (CUDA-graph replays)
-};
-
-static DropCfg make_drop(float p, uint64_t seed, const uint64_t* seed_dev) {
-  DropCfg c;
-  if (p <= 0.f) { c.thresh = 0; c.scale = 1.f; }
-  else {
-    long t = lround(static_cast<double>(p) * 65536.0);
-    c.thresh = static_cast<uint32_t>(t < 1 ? 1 : (t > 65535 ? 65535 : t));
-    c.scale = static_cast<float>(65536.0 / (65536.0 - c.thresh));     // unbiased for the quantised keep rate
-  }
-  c.seed = seed;
-  c.seed_dev = seed_dev;
-  return c;
-}
 
 // Gather one tile of z1 = drop(relu(pd[src] + ps[dst])) into shared memory, layout Z[p][H1].
 // One warp per pair at a time, a lane owns 4 consecutive hidden units (one float4 per operand row).
@@ -91,7 +70,7 @@ constexpr int kFwdTile = 128;
 constexpr size_t kFwdSmem = (static_cast<size_t>(H1) * H2 + static_cast<size_t>(kFwdTile) * H1) * sizeof(float);
 
 __global__ void __launch_bounds__(kDecThreads, 2)
-decoder_fwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int64_t n_pairs,
+decoder_fwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, const int* __restrict__ perm, int64_t n_pairs,
                    const float* __restrict__ pd, const float* __restrict__ ps, const float* __restrict__ w2,
                    const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3,
                    DropCfg drop, float* __restrict__ out, float* __restrict__ z2_save) {
@@ -155,7 +134,7 @@ decoder_fwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int
       float part = z2[0] * wv3.x + z2[1] * wv3.y + z2[2] * wv3.z + z2[3] * wv3.w;
 #pragma unroll
       for (int o = 8; o; o >>= 1) part += __shfl_xor_sync(kFull, part, o);   // fixed tree: deterministic
-      if (tj == 0 && e < n_pairs) out[e] = part + bias3;
+      if (tj == 0 && e < n_pairs) out[perm ? perm[e] : e] = part + bias3;
     }
   }
 }
@@ -169,12 +148,11 @@ decoder_fwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int
 // Per-CTA partials go to the workspace and are summed in CTA order by decoder_reduce_partials.
 // ------------------------------------------------------------------------------------------------
 constexpr int kBwdTile = 64;
-constexpr int kPartial = H2 * H1 + 3 * H2;   // dW2 | db2 | dw3 | db3 (first slot of the last H2 block)
 constexpr size_t kBwdSmem = (static_cast<size_t>(H2) * H1 + static_cast<size_t>(kBwdTile) * H1 +
                              static_cast<size_t>(kBwdTile) * H2 + kBwdTile) * sizeof(float);
 
 __global__ void __launch_bounds__(kDecThreads, 2)
-decoder_bwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int64_t n_pairs,
+decoder_bwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, const int* __restrict__ perm, int64_t n_pairs,
                    const float* __restrict__ pd, const float* __restrict__ ps, const float* __restrict__ w2,
                    const float* __restrict__ w3, DropCfg drop, const float* __restrict__ z2,
                    const float* __restrict__ dout, float* __restrict__ dz1, float* __restrict__ partials) {
@@ -206,7 +184,7 @@ decoder_bwd_kernel(const int* __restrict__ src, const int* __restrict__ dst, int
     const int64_t base = tile * kBwdTile;
     __syncthreads();
     gather_z1_tile<kBwdTile>(src, dst, base, n_pairs, pd, ps, drop, Z);
-    if (t < kBwdTile) DO[t] = (base + t < n_pairs) ? dout[base + t] : 0.f;
+    if (t < kBwdTile) DO[t] = (base + t < n_pairs) ? dout[perm ? perm[base + t] : base + t] : 0.f;
     __syncthreads();
     // ---- dz2 tile + db2 / dw3 / db3 partials -------------------------------------------------
 #pragma unroll
@@ -328,6 +306,12 @@ __global__ void decoder_reduce_partials(const float* __restrict__ partials, int 
   else db3[0] = s;
 }
 
+// DG_DECODER=simt selects the fp32 FMA kernels below (A/B runs); the default is the tcgen05 path (decoder_tc.cu)
+static bool use_simt_decoder() {
+  const char* v = getenv("DG_DECODER");
+  return v && strcmp(v, "simt") == 0;
+}
+
 static int decoder_grid(int64_t n_tiles) {
   int64_t g = static_cast<int64_t>(kNumSM) * 2;     // 2 resident CTAs per SM
   if (n_tiles < g) g = n_tiles;
@@ -338,13 +322,16 @@ static int decoder_grid(int64_t n_tiles) {
 
 extern "C" {
 
-int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, const float* pd, const float* ps,
+int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_pairs, const float* pd, const float* ps,
                        const float* w2, const float* b2, const float* w3, const float* b3, float dropout_p,
                        uint64_t seed, const uint64_t* seed_dev, float* out, float* z2_save, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(n_pairs >= 0, "n_pairs < 0");
   DG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p must be in [0,1)");
   if (n_pairs == 0) return DG_OK;
+  if (!use_simt_decoder())
+    return launch_decoder_fwd_tc(src, dst, perm, n_pairs, pd, ps, w2, b2, w3, b3, make_drop(dropout_p, seed, seed_dev), out, z2_save,
+                                 as_stream(stream));
   static bool attr_set = false;
   if (!attr_set) {
     DG_CHECK_CUDA(cudaFuncSetAttribute(decoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFwdSmem)));
@@ -352,7 +339,7 @@ int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, 
   }
   const int64_t n_tiles = (n_pairs + kFwdTile - 1) / kFwdTile;
   decoder_fwd_kernel<<<decoder_grid(n_tiles), kDecThreads, kFwdSmem, as_stream(stream)>>>(
-      src, dst, n_pairs, pd, ps, w2, b2, w3, b3, make_drop(dropout_p, seed, seed_dev), out, z2_save);
+      src, dst, perm, n_pairs, pd, ps, w2, b2, w3, b3, make_drop(dropout_p, seed, seed_dev), out, z2_save);
   DG_CHECK_LAUNCH("decoder_fwd");
   return DG_OK;
 }
@@ -362,7 +349,7 @@ size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs) {
   return dg::ws_add(0, static_cast<size_t>(dg::kNumSM) * 2 * dg::kPartial * sizeof(float));
 }
 
-int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, const float* pd, const float* ps,
+int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_pairs, const float* pd, const float* ps,
                        const float* w2, const float* w3, float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* z2,
                        const float* dout, float* dz1, float* dw2, float* db2, float* dw3, float* db3,
                        void* workspace, size_t workspace_bytes, dg_stream_t stream) {
@@ -372,16 +359,22 @@ int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs, 
   Workspace w(workspace, workspace_bytes);
   float* partials = w.take<float>(static_cast<size_t>(kNumSM) * 2 * kPartial);
   if (!partials) { set_error("decoder_bwd: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    DG_CHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBwdSmem)));
-    attr_set = true;
+  int grid = 0;
+  if (!use_simt_decoder()) {
+    DG_PROPAGATE(launch_decoder_bwd_tc(src, dst, perm, n_pairs, pd, ps, w2, w3, make_drop(dropout_p, seed, seed_dev), z2, dout, dz1,
+                                       partials, &grid, as_stream(stream)));
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DG_CHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBwdSmem)));
+      attr_set = true;
+    }
+    const int64_t n_tiles = (n_pairs + kBwdTile - 1) / kBwdTile;
+    grid = decoder_grid(n_tiles);
+    decoder_bwd_kernel<<<grid, kDecThreads, kBwdSmem, as_stream(stream)>>>(
+        src, dst, perm, n_pairs, pd, ps, w2, w3, make_drop(dropout_p, seed, seed_dev), z2, dout, dz1, partials);
+    DG_CHECK_LAUNCH("decoder_bwd");
   }
-  const int64_t n_tiles = (n_pairs + kBwdTile - 1) / kBwdTile;
-  const int grid = decoder_grid(n_tiles);
-  decoder_bwd_kernel<<<grid, kDecThreads, kBwdSmem, as_stream(stream)>>>(
-      src, dst, n_pairs, pd, ps, w2, w3, make_drop(dropout_p, seed, seed_dev), z2, dout, dz1, partials);
-  DG_CHECK_LAUNCH("decoder_bwd");
   constexpr int kOut = H2 * H1 + 2 * H2 + 1;
   decoder_reduce_partials<<<(kOut + 255) / 256, 256, 0, as_stream(stream)>>>(partials, grid, dw2, db2, dw3, db3);
   DG_CHECK_LAUNCH("decoder_reduce_partials");

@@ -10,6 +10,8 @@ Reference call sites replaced (citations into /root/reference):
   * `csr_dropout`                      th.randperm edge dropout + graph rebuild (augmentation.py:35-124)
   * `topk_rows`, `knn_graph_from_neighbors`   np.argpartition + scipy A+A^T+I, D^-1 A (data_loader.py:291-308)
 """
+import os
+
 import torch as th
 
 from . import _lib as L
@@ -243,12 +245,17 @@ def spmm(csr, x, src_scale=None, dst_scale=None, bias=None, relu=False, tag='spm
 # ------------------------------------------------------------------------------------------------
 class PairGraph:
     """Scored (drug, disease) pairs in label order + the two segment structures the deterministic
-    backward needs (CSR by drug and by disease whose `indices` are pair ids)."""
+    backward needs (CSR by drug and by disease whose `indices` are pair ids).
+
+    `processing_order()` is the optional by-drug walk (DG_DECODER_ORDER=by-drug): the pairs sorted by drug once
+    per graph (stable, so the order is a pure function of the pair list), which turns the pd-row gather into a
+    re-read of the row the previous pair used and leaves only the ps rows (n_dst x 512 B) as a random gather that
+    L2 holds. The kernel scatters the logits back to label order (`perm`), so callers never see the difference."""
 
     def __init__(self, src, dst, n_src, n_dst):
         self.src, self.dst = _i32(src, 'src'), _i32(dst, 'dst')
         self.n_src, self.n_dst = int(n_src), int(n_dst)
-        self._by_src = self._by_dst = None
+        self._by_src = self._by_dst = self._order = None
 
     @property
     def n_pairs(self):
@@ -269,6 +276,24 @@ class PairGraph:
             self._by_dst = self._segments(self.dst, self.n_dst)
         return self._by_dst
 
+    def processing_order(self):
+        """(perm, src_p, dst_p, seg_src, seg_dst): perm[i] = label position of the i-th processed pair (pairs
+        sorted by drug, ties in label order), the endpoint arrays in that order, and the two segment CSRs over
+        processing positions (seg_src's indices are simply 0..E-1: each drug's pairs are contiguous)."""
+        if self._order is None:
+            perm = self._segments(self.src, self.n_src).indices
+            long_perm = perm.long()
+            src_p, dst_p = self.src[long_perm].contiguous(), self.dst[long_perm].contiguous()
+            self._order = (perm, src_p, dst_p, self._segments(src_p, self.n_src), self._segments(dst_p, self.n_dst))
+        return self._order
+
+
+def _decoder_by_drug():
+    """DG_DECODER_ORDER=by-drug walks the pairs sorted by drug instead of in label order (see
+    PairGraph.processing_order; measured neutral while the kernels are not gather-bound, so label order, which
+    needs no permutation, is the default)."""
+    return os.environ.get('DG_DECODER_ORDER', 'label') == 'by-drug'
+
 
 class DecoderFunction(th.autograd.Function):
     @staticmethod
@@ -285,7 +310,10 @@ class DecoderFunction(th.autograd.Function):
         seed_val = 0 if seed_dev is not None else int(seed)
         out = th.empty(e, dtype=th.float32, device=pd.device)
         z2 = th.empty((e, DEC_H2), dtype=th.float32, device=pd.device) if save else None
-        L.check(lib.dg_decoder_fwd_f32(L.ptr(pairs.src), L.ptr(pairs.dst), e, L.ptr(pd, th.float32, 'pd'),
+        by_drug = e and _decoder_by_drug()
+        perm, src_p, dst_p = pairs.processing_order()[:3] if by_drug else (None, pairs.src, pairs.dst)
+        ctx.by_drug = by_drug
+        L.check(lib.dg_decoder_fwd_f32(L.ptr(src_p), L.ptr(dst_p), L.ptr(perm), e, L.ptr(pd, th.float32, 'pd'),
                                        L.ptr(ps, th.float32, 'ps'), L.ptr(w2, th.float32), L.ptr(b2, th.float32),
                                        L.ptr(w3, th.float32), L.ptr(b3, th.float32), float(p), seed_val, L.ptr(seed_dev), L.ptr(out),
                                        L.ptr(z2), L.stream()), 'decoder_fwd')
@@ -309,13 +337,15 @@ class DecoderFunction(th.autograd.Function):
         dw3 = th.empty((1, DEC_H2), dtype=th.float32, device=dev)
         db3 = th.empty(1, dtype=th.float32, device=dev)
         ws = L.workspace(lib.dg_decoder_bwd_workspace_bytes(e), dev)
-        L.check(lib.dg_decoder_bwd_f32(L.ptr(pairs.src), L.ptr(pairs.dst), e, L.ptr(pd), L.ptr(ps), L.ptr(w2),
+        perm, src_p, dst_p, seg_src, seg_dst = pairs.processing_order() if ctx.by_drug else (None, pairs.src, pairs.dst,
+                                                                                             pairs.by_src(), pairs.by_dst())
+        L.check(lib.dg_decoder_bwd_f32(L.ptr(src_p), L.ptr(dst_p), L.ptr(perm), e, L.ptr(pd), L.ptr(ps), L.ptr(w2),
                                        L.ptr(w3), ctx.p, ctx.seed, L.ptr(ctx.seed_dev), L.ptr(z2), L.ptr(dout, th.float32, 'dout'),
                                        L.ptr(dz1), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3), L.ptr(ws),
                                        ws.numel(), L.stream()), 'decoder_bwd')
-        # scatter of dz1 into node gradients = two segment sums in fixed order (no atomics)
-        dpd = _spmm_raw(pairs.by_src(), dz1, tag='decoder.seg') if ctx.needs_input_grad[0] else None
-        dps = _spmm_raw(pairs.by_dst(), dz1, tag='decoder.seg') if ctx.needs_input_grad[1] else None
+        # scatter of dz1 (processing order) into node gradients = two segment sums in fixed order (no atomics)
+        dpd = _spmm_raw(seg_src, dz1, tag='decoder.seg') if ctx.needs_input_grad[0] else None
+        dps = _spmm_raw(seg_dst, dz1, tag='decoder.seg') if ctx.needs_input_grad[1] else None
         return dpd, dps, dw2, db2, dw3, db3, None, None, None, None
 
 

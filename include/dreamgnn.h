@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 1
+#define DG_ABI_VERSION 2
 
 #define DG_OK 0
 #define DG_ERR_INVALID_ARGUMENT (-1)
@@ -130,10 +130,15 @@ DG_API int dg_spmm_csr_bf16(const int32_t* indptr, const int32_t* indices, const
  * Hidden widths 128 / 64 are fixed by the reference (layers.py:349-351). Dropout uses a counter
  * based generator keyed by (seed, pair, unit); p == 0 disables it (eval mode). When `seed_dev` is non-NULL
  * the seed is read from that device word instead of `seed`, so a captured CUDA graph draws a fresh mask
- * on every replay. */
+ * on every replay.
+ * `perm` (nullable, [n_pairs]): src/dst are given in a caller-chosen processing order and perm[i] is the label
+ * position of the i-th processed pair -- out[perm[i]] receives its logit and the backward reads dout[perm[i]];
+ * z2_save and dz1 stay in processing order. The host sorts the pairs by drug once per decoder graph, so
+ * consecutive pairs share their pd row and only the ps rows are a random gather (the label-order gather of both
+ * operands misses L2 at the 20M-pair shape: 77 MB of node rows against ~63 MB of L2 per die). NULL = identity. */
 #define DG_DEC_H1 128
 #define DG_DEC_H2 64
-DG_API int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
+DG_API int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_pairs,
                        const float* pd, const float* ps, const float* w2, const float* b2,
                        const float* w3, const float* b3, float dropout_p, uint64_t seed,
                        const uint64_t* seed_dev, float* out, float* z2_save /* nullable: [n_pairs,64] kept for backward */,
@@ -144,7 +149,7 @@ DG_API int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, int64_t n_
  * segment sums of dz1 over the decoder graph's CSR / CSC (dg_spmm_csr_f32 with indices = edge ids)
  * -- no atomics. */
 DG_API size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs);
-DG_API int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, int64_t n_pairs,
+DG_API int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_pairs,
                        const float* pd, const float* ps, const float* w2, const float* w3,
                        float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* z2,
                        const float* dout,

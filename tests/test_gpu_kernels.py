@@ -195,8 +195,12 @@ def _decoder_params(gen, n_in):
     return P
 
 
+@pytest.mark.parametrize('impl,order', [('tc', 'label'), ('tc', 'by-drug'), ('simt', 'label')])
 @pytest.mark.parametrize('n_pairs', [0, 1, 63, 128, 1000, 40000])
-def test_decoder_forward_backward(dev, n_pairs):
+def test_decoder_forward_backward(dev, n_pairs, impl, order, monkeypatch):
+    """impl: the tcgen05 kernels (default) or the fp32 FMA ones; order: label order or the by-drug walk."""
+    monkeypatch.setenv('DG_DECODER', impl)
+    monkeypatch.setenv('DG_DECODER_ORDER', order)
     from dreamgnn_b200.layers import MLPDecoder
     from dreamgnn_b200 import graph as G
     gen = th.Generator().manual_seed(n_pairs)
@@ -233,9 +237,11 @@ def test_decoder_forward_backward(dev, n_pairs):
     assert th.equal(hdg.grad, g1)
 
 
-def test_decoder_dropout_is_consistent_between_forward_and_backward(dev):
+@pytest.mark.parametrize('order', ['label', 'by-drug'])
+def test_decoder_dropout_is_consistent_between_forward_and_backward(dev, order, monkeypatch):
     """Training mode: the backward regenerates the forward's masks. Checked as a directional derivative of
     the (piecewise-linear, fixed-seed) function, plus the keep rate and the 1/(1-p) scaling."""
+    monkeypatch.setenv('DG_DECODER_ORDER', order)
     o = ops()
     gen = th.Generator().manual_seed(7)
     n_d, n_s, e, p = 50, 40, 6000, 0.3
@@ -257,7 +263,10 @@ def test_decoder_dropout_is_consistent_between_forward_and_backward(dev):
     eps = 1e-3
     fd = ((f(pd + eps * dpd, w2 + eps * dw2).double() - f(pd - eps * dpd, w2 - eps * dw2).double()) * gout).sum() / (2 * eps)
     an = (pd_g.grad.double() * dpd).sum() + (w2_g.grad.double() * dw2).sum()
-    assert abs(float(fd - an)) <= 2e-2 * abs(float(an)) + 1e-3
+    # the directional derivative can be small next to the gradient (cancellation): scale the tolerance by the
+    # Cauchy-Schwarz bound of the two inner products, not by |an|
+    scale = float(pd_g.grad.double().norm() * dpd.double().norm() + w2_g.grad.double().norm() * dw2.double().norm())
+    assert abs(float(fd - an)) <= 5e-3 * scale
     # keep-rate of the first dropout: eval/(train) ratio on a linear probe
     z2 = th.empty(e, 64, device=dev)
     lib = o.L.load()
@@ -266,7 +275,7 @@ def test_decoder_dropout_is_consistent_between_forward_and_backward(dev):
     # keep every operand alive until the launch is enqueued (temporaries would be recycled by the allocator)
     zs, w_ones, b_zero, w3_ones, b3_zero = (th.zeros_like(ps), th.ones(64, 128, device=dev), th.zeros(64, device=dev),
                                             th.ones(64, device=dev), th.zeros(1, device=dev))
-    o.L.check(lib.dg_decoder_fwd_f32(o.L.ptr(pairs.src), o.L.ptr(pairs.dst), e, o.L.ptr(big), o.L.ptr(zs), o.L.ptr(w_ones),
+    o.L.check(lib.dg_decoder_fwd_f32(o.L.ptr(pairs.src), o.L.ptr(pairs.dst), None, e, o.L.ptr(big), o.L.ptr(zs), o.L.ptr(w_ones),
                                      o.L.ptr(b_zero), o.L.ptr(w3_ones), o.L.ptr(b3_zero), p, 42, None, o.L.ptr(outp), o.L.ptr(z2),
                                      o.L.stream()), 'decoder_fwd')
     th.cuda.synchronize()
