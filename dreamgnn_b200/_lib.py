@@ -39,6 +39,8 @@ _SIGNATURES = {
     'dg_gemm_nt_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
     'dg_gemm_nt_f32': (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64,
                                c_int64, _P, c_int, _P, c_size_t, _P]),
+    'dg_gemm_f32': (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
+                            c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
     'dg_topk_rows_f64': (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P]),
     'dg_knn_graph_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'dg_knn_graph_from_neighbors': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -12,6 +12,11 @@
 //   * long-K / small-output shapes (the weight-gradient GEMMs, K = number of nodes) are split along K into
 //     per-CTA partial tiles that a second kernel sums in a fixed order (deterministic, no atomics).
 //
+//   * either operand may also be given "transposed" ([K, M] / [K, N] row-major, i.e. MN-major for the tensor core):
+//     TMA lands 32-column x 32-row boxes in the 128-byte swizzle with a 32-byte atom -- the only MN-major layout
+//     fp32 / tf32 operands have -- and the instruction descriptor's major bits select it, so the weight-gradient
+//     GEMMs dW = X^T dY read X and dY as stored (no transposed copies).
+//
 // Replaces the cuBLAS calls behind th.mm / th.matmul at layers.py:120-121, 220-221 (W_r projections),
 // layers.py:311 (FGCN support = x @ W) and their backward GEMMs.
 #include <cuda.h>
@@ -37,6 +42,7 @@ struct GemmParams {
   const float* row_scale;  // nullable, [batch * M]
   int64_t ldc, stride_c;
   int M, N, nkb, kb_per_split, splits, a_batched, b_batched, vec_ok, n_tiles;
+  int a_mn, b_mn;          // operand stored [K, M] / [K, N] (MN-major) instead of [M, K] / [N, K]
 };
 
 template <bool kSplit3>
@@ -95,8 +101,17 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t bar = full0 + 8 * s;
         mbar_expect_tx(bar, 2 * kTileBytes);
         const int k = (kb0 + it) * kBK;
-        tma_load_3d(dst, &tmA, bar, k, m0, za);                                      // raw fp32 A tile -> becomes A_hi
-        tma_load_3d(dst + (kSplit3 ? 2 : 1) * kTileBytes, &tmB, bar, k, n0, zb);     // raw fp32 B tile -> becomes B_hi
+        // raw fp32 tiles (they become A_hi / B_hi). K-major: one 32 (k) x 128 (rows) box; MN-major: four 32 (mn) x
+        // 32 (k) boxes, one per 32-column block of the tile (4 KB each)
+        const uint32_t dst_b = dst + (kSplit3 ? 2 : 1) * kTileBytes;
+        if (!p.a_mn) tma_load_3d(dst, &tmA, bar, k, m0, za);
+        else
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_3d(dst + i * (kTileBytes / 4), &tmA, bar, m0 + 32 * i, k, za);
+        if (!p.b_mn) tma_load_3d(dst_b, &tmB, bar, k, n0, zb);
+        else
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_3d(dst_b + i * (kTileBytes / 4), &tmB, bar, n0 + 32 * i, k, zb);
       }
     }
   } else if (warp == 1) {
@@ -107,20 +122,26 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait((kSplit3 ? ready0 : full0) + 8 * s, round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t base = smem_u32(smem + s * kStageBytes);
-        const uint64_t a_hi = smem_desc_sw128(base);
-        const uint64_t a_lo = smem_desc_sw128(base + kTileBytes);
-        const uint64_t b_hi = smem_desc_sw128(base + (kSplit3 ? 2 : 1) * kTileBytes);
-        const uint64_t b_lo = smem_desc_sw128(base + 3 * kTileBytes);
+        const uint32_t base_b = base + (kSplit3 ? 2 : 1) * kTileBytes;
+        // MN-major tiles: 4 blocks of [32 k-rows][128 B] (LBO = 4 KB between blocks, 4-row swizzle atoms 512 B apart)
+        const uint64_t a_hi = p.a_mn ? smem_desc_mn32(base, kTileBytes / 4, 512) : smem_desc_sw128(base);
+        const uint64_t a_lo = p.a_mn ? smem_desc_mn32(base + kTileBytes, kTileBytes / 4, 512) : smem_desc_sw128(base + kTileBytes);
+        const uint64_t b_hi = p.b_mn ? smem_desc_mn32(base_b, kTileBytes / 4, 512) : smem_desc_sw128(base_b);
+        const uint64_t b_lo = p.b_mn ? smem_desc_mn32(base + 3 * kTileBytes, kTileBytes / 4, 512) : smem_desc_sw128(base + 3 * kTileBytes);
+        // one UMMA consumes K = 8 tf32: 32 bytes along a K-major row (+2 in the address field), 8 rows = 1 KB of an
+        // MN-major block (+64)
+        const uint32_t ka = p.a_mn ? 64u : 2u, kb = p.b_mn ? 64u : 2u;
+        const uint32_t idesc = kInstrDesc | (static_cast<uint32_t>(p.a_mn) << 15) | (static_cast<uint32_t>(p.b_mn) << 16);
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k) {                     // UMMA_K = 8 tf32 = 32 bytes -> +2 in the address field
+        for (int k = 0; k < kBK / 8; ++k) {
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
           if (kSplit3) {
             // small terms first, the dominant product last
-            umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, kInstrDesc, acc);
-            umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, kInstrDesc, 1u);
-            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, kInstrDesc, 1u);
+            umma_tf32(tmem_base, a_lo + ka * k, b_hi + kb * k, idesc, acc);
+            umma_tf32(tmem_base, a_hi + ka * k, b_lo + kb * k, idesc, 1u);
+            umma_tf32(tmem_base, a_hi + ka * k, b_hi + kb * k, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, kInstrDesc, acc);
+            umma_tf32(tmem_base, a_hi + ka * k, b_hi + kb * k, idesc, acc);
           }
         }
         umma_commit(empty0 + 8 * s);                            // frees the stage once these MMAs retire
@@ -265,16 +286,19 @@ static EncodeTiledFn encode_fn() {
 
 // [batch, rows, k] fp32 tensor with row stride `ld` and batch stride `bstride` (elements); box = 32 (k) x 128
 // (rows) x 1, 128-byte swizzle, out-of-bounds -> 0 (ragged M / N / K edges need no special casing)
-static int make_map(CUtensorMap* map, const float* base, int rows, int k, int64_t ld, int64_t bstride, int batch) {
+// With mn_major the tensor is [batch, k, rows] (rows contiguous): box = 32 (rows) x 32 (k) x 1 in the 128-byte swizzle
+// with a 32-byte atom.
+static int make_map(CUtensorMap* map, const float* base, int rows, int k, int64_t ld, int64_t bstride, int batch, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("gemm: cuTensorMapEncodeTiled not available from the driver"); return DG_ERR_UNSUPPORTED; }
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(batch > 1 ? bstride : ld * rows) * 4};
-  cuuint32_t box[3] = {kBK, kBM, 1};
+  const int inner = mn_major ? rows : k, outer = mn_major ? k : rows;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer), static_cast<cuuint64_t>(batch)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(batch > 1 ? bstride : ld * outer) * 4};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(mn_major ? kBK : kBM), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gemm: cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return DG_ERR_INVALID_ARGUMENT; }
   return DG_OK;
 }
@@ -317,20 +341,21 @@ extern "C" {
 size_t dg_gemm_nt_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, int a_batched, int b_batched) {
   using namespace dg;
   GemmPlan g = plan_gemm(M, N, K, batch);
+  const size_t mp = static_cast<size_t>((M + 3) / 4 * 4), np = static_cast<size_t>((N + 3) / 4 * 4);
   size_t b = 0;                                              // worst case: both operands need the packing copy
-  b = ws_add(b, static_cast<size_t>(a_batched ? batch : 1) * M * g.kp * 4);
-  b = ws_add(b, static_cast<size_t>(b_batched ? batch : 1) * N * g.kp * 4);
+  b = ws_add(b, static_cast<size_t>(a_batched ? batch : 1) * mp * g.kp * 4);   // covers [M, Kp] and [K, Mp]
+  b = ws_add(b, static_cast<size_t>(b_batched ? batch : 1) * np * g.kp * 4);
   b = ws_add(b, g.partial_elems * 4);
   return b;
 }
 
-int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B, int64_t ldb, int64_t stride_b, float* C,
-                   int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch, const float* row_scale,
-                   int precision, void* workspace, size_t workspace_bytes, dg_stream_t stream) {
+int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_a, const float* B, int64_t ldb, int64_t stride_b,
+                int trans_b, float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch,
+                const float* row_scale, int precision, void* workspace, size_t workspace_bytes, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "M, N, K, batch must be positive");
   DG_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31) && batch < 65536, "shape too large");
-  DG_REQUIRE(lda >= K && ldb >= K && ldc >= N, "leading dimension too small");
+  DG_REQUIRE(lda >= (trans_a ? M : K) && ldb >= (trans_b ? N : K) && ldc >= N, "leading dimension too small");
   DG_REQUIRE(precision == 0 || precision == 1, "precision: 0 = 3xTF32 (fp32-accurate), 1 = single TF32");
   cudaStream_t st = as_stream(stream);
   const int a_copies = (stride_a != 0 && batch > 1) ? static_cast<int>(batch) : 1;
@@ -340,30 +365,35 @@ int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B
   const bool split3 = precision == 0;
   Workspace w(workspace, workspace_bytes);
   auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return static_cast<unsigned>(b > 148 * 16 ? 148 * 16 : (b ? b : 1)); };
-  int64_t ka = K, kb = K;
-  if (!tma_addressable(A, lda, stride_a, a_copies)) {
-    float* pa = w.take<float>(static_cast<size_t>(a_copies) * M * g.kp);
-    if (!pa) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
-    pack_rows_kernel<<<dim3(blocks(static_cast<size_t>(M) * g.kp), a_copies), 256, 0, st>>>(A, lda, stride_a, static_cast<int>(M), static_cast<int>(K), g.kp, pa);
-    DG_CHECK_LAUNCH("pack_rows(A)");
-    A = pa; lda = g.kp; stride_a = M * g.kp; ka = g.kp;
-  }
-  if (!tma_addressable(B, ldb, stride_b, b_copies)) {
-    float* pb = w.take<float>(static_cast<size_t>(b_copies) * N * g.kp);
-    if (!pb) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
-    pack_rows_kernel<<<dim3(blocks(static_cast<size_t>(N) * g.kp), b_copies), 256, 0, st>>>(B, ldb, stride_b, static_cast<int>(N), static_cast<int>(K), g.kp, pb);
-    DG_CHECK_LAUNCH("pack_rows(B)");
-    B = pb; ldb = g.kp; stride_b = N * g.kp; kb = g.kp;
-  }
+  // an operand TMA cannot address directly (row stride not a multiple of 16 bytes or a misaligned base) is first
+  // packed into the workspace with the same orientation: [rows, k] -> [rows, kp], or [k, rows] -> [k, rows_p]
+  struct Op { const float* p; int64_t ld, stride; int rows, k; };
+  auto prepare = [&](Op& o, int copies, bool trans, const char* what) -> int {
+    if (tma_addressable(o.p, o.ld, o.stride, copies)) return DG_OK;
+    const int outer = trans ? o.k : o.rows, inner = trans ? o.rows : o.k;
+    const int inner_p = (inner + 3) / 4 * 4;
+    float* packed = w.take<float>(static_cast<size_t>(copies) * outer * inner_p);
+    if (!packed) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
+    pack_rows_kernel<<<dim3(blocks(static_cast<size_t>(outer) * inner_p), copies), 256, 0, st>>>(o.p, o.ld, o.stride, outer, inner,
+                                                                                             inner_p, packed);
+    DG_CHECK_LAUNCH(what);
+    o.p = packed; o.ld = inner_p; o.stride = static_cast<int64_t>(outer) * inner_p;
+    if (trans) o.rows = inner_p; else o.k = inner_p;          // the zero padding is part of the tensor map's extent
+    return DG_OK;
+  };
+  Op oa{A, lda, stride_a, static_cast<int>(M), static_cast<int>(K)}, ob{B, ldb, stride_b, static_cast<int>(N), static_cast<int>(K)};
+  DG_PROPAGATE(prepare(oa, a_copies, trans_a != 0, "pack_rows(A)"));
+  DG_PROPAGATE(prepare(ob, b_copies, trans_b != 0, "pack_rows(B)"));
   float* partial = g.partial_elems ? w.take<float>(g.partial_elems) : nullptr;
   if (g.partial_elems && !partial) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
   CUtensorMap mA, mB;
-  DG_PROPAGATE(make_map(&mA, A, static_cast<int>(M), static_cast<int>(ka), lda, stride_a, a_copies));
-  DG_PROPAGATE(make_map(&mB, B, static_cast<int>(N), static_cast<int>(kb), ldb, stride_b, b_copies));
+  DG_PROPAGATE(make_map(&mA, oa.p, oa.rows, oa.k, oa.ld, oa.stride, a_copies, trans_a != 0));
+  DG_PROPAGATE(make_map(&mB, ob.p, ob.rows, ob.k, ob.ld, ob.stride, b_copies, trans_b != 0));
   GemmParams p;
   p.C = C; p.partial = partial; p.row_scale = row_scale; p.ldc = ldc; p.stride_c = stride_c;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.nkb = g.nkb; p.kb_per_split = g.kb_per_split; p.splits = g.splits;
   p.a_batched = a_copies > 1 ? 1 : 0; p.b_batched = b_copies > 1 ? 1 : 0;
+  p.a_mn = trans_a ? 1 : 0; p.b_mn = trans_b ? 1 : 0;
   p.vec_ok = (g.splits > 1) ? (N % 4 == 0)
                             : ((ldc % 4 == 0) && (stride_c % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0));
   p.n_tiles = static_cast<int>((N + kBN - 1) / kBN);
@@ -379,7 +409,7 @@ int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B
     if (!attr) { DG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
     gemm_nt_tf32_kernel<false><<<grid, kGemmThreads, smem, st>>>(mA, mB, p);
   }
-  DG_CHECK_LAUNCH("gemm_nt_tf32");
+  DG_CHECK_LAUNCH("gemm_tf32");
   if (g.splits > 1) {
     size_t per = static_cast<size_t>(M) * N;
     unsigned nb = static_cast<unsigned>((per + 255) / 256 > 148 * 8 ? 148 * 8 : (per + 255) / 256);
@@ -387,5 +417,12 @@ int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B
     DG_CHECK_LAUNCH("splitk_reduce");
   }
   return DG_OK;
+}
+
+int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const float* B, int64_t ldb, int64_t stride_b, float* C,
+                   int64_t ldc, int64_t stride_c, int64_t M, int64_t N, int64_t K, int64_t batch, const float* row_scale,
+                   int precision, void* workspace, size_t workspace_bytes, dg_stream_t stream) {
+  return dg_gemm_f32(A, lda, stride_a, 0, B, ldb, stride_b, 0, C, ldc, stride_c, M, N, K, batch, row_scale, precision, workspace,
+                     workspace_bytes, stream);
 }
 }

@@ -404,29 +404,36 @@ def gemm_backend():
     return _os.environ.get('DG_GEMM', 'tcgen05')
 
 
-def gemm_nt(a, b, row_scale=None, precision=0):
-    """C[r] = diag(row_scale[r]) * A[r] @ B[r]^T on the tensor cores. a: [M,K] or [R,M,K]; b: [N,K] or [R,N,K]
-    (a 2-D operand is shared by all batches). fp32 in, fp32 out; precision 0 = 3xTF32 (fp32-level accuracy)."""
+def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, precision=0):
+    """C[r] = diag(row_scale[r]) * op(A[r]) @ op(B[r])^T on the tensor cores, op(A) [M,K], op(B) [N,K].
+    a: [M,K] ([K,M] with trans_a) or batched [R,..]; b: [N,K] ([K,N] with trans_b) or batched (a 2-D operand is shared
+    by all batches). Transposed operands are read as stored (MN-major tensor-core operands): no copy.
+    fp32 in, fp32 out; precision 0 = 3xTF32 (fp32-level accuracy)."""
     lib = L.load()
     if a.dtype != th.float32 or b.dtype != th.float32:
-        raise TypeError('gemm_nt: fp32 operands expected')
+        raise TypeError('gemm: fp32 operands expected')
     batch = max(a.shape[0] if a.dim() == 3 else 1, b.shape[0] if b.dim() == 3 else 1)
     a, b = a.contiguous(), b.contiguous()
-    M, K = a.shape[-2], a.shape[-1]
-    N = b.shape[-2]
-    if b.shape[-1] != K:
-        raise ValueError('gemm_nt: inner dimensions differ')
+    (K, M) = a.shape[-2:] if trans_a else a.shape[-2:][::-1]
+    (Kb, N) = b.shape[-2:] if trans_b else b.shape[-2:][::-1]
+    if Kb != K:
+        raise ValueError('gemm: inner dimensions differ')
     a_b, b_b = int(a.dim() == 3 and batch > 1), int(b.dim() == 3 and batch > 1)
     out = th.empty((batch, M, N) if (a.dim() == 3 or b.dim() == 3) else (M, N), dtype=th.float32, device=a.device)
     ws = L.workspace(lib.dg_gemm_nt_workspace_bytes(M, N, K, batch, a_b or batch == 1, b_b or batch == 1), a.device)
     if row_scale is not None:
         row_scale = row_scale.reshape(-1).to(th.float32).contiguous()
         if row_scale.numel() != batch * M:
-            raise ValueError('gemm_nt: row_scale must have batch*M elements')
-    L.check(lib.dg_gemm_nt_f32(L.ptr(a), K, M * K if a_b else 0, L.ptr(b), K, N * K if b_b else 0, L.ptr(out), N, M * N,
-                               M, N, K, batch, L.ptr(row_scale), int(precision), L.ptr(ws), ws.numel(), L.stream()),
-            'gemm_nt')
+            raise ValueError('gemm: row_scale must have batch*M elements')
+    L.check(lib.dg_gemm_f32(L.ptr(a), a.shape[-1], M * K if a_b else 0, int(trans_a), L.ptr(b), b.shape[-1], N * K if b_b else 0,
+                            int(trans_b), L.ptr(out), N, M * N, M, N, K, batch, L.ptr(row_scale), int(precision), L.ptr(ws),
+                            ws.numel(), L.stream()), 'gemm')
     return out
+
+
+def gemm_nt(a, b, row_scale=None, precision=0):
+    """C[r] = diag(row_scale[r]) * A[r] @ B[r]^T with a: [M,K] or [R,M,K]; b: [N,K] or [R,N,K]."""
+    return gemm(a, b, False, False, row_scale, precision)
 
 
 class ProjectFunction(th.autograd.Function):
@@ -435,7 +442,7 @@ class ProjectFunction(th.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        return gemm_nt(x, w.transpose(1, 2))                    # B[r] = w[r]^T  [N,K], K-major
+        return gemm(x, w, trans_b=True)                         # w[r] is [K,N]: read MN-major, no transpose
 
     @staticmethod
     def backward(ctx, dy):
@@ -447,8 +454,9 @@ class ProjectFunction(th.autograd.Function):
             R, M, N = dy.shape
             dx = gemm_nt(dy.permute(1, 0, 2).reshape(M, R * N), w.permute(1, 0, 2).reshape(w.shape[1], R * N))
         if ctx.needs_input_grad[1]:
-            # dw[r] = x^T @ dy[r]: A = x^T [K,M] shared, B[r] = dy[r]^T [N,M]; long K = M -> split-K inside
-            dw = gemm_nt(x.t(), dy.transpose(1, 2))
+            # dw[r] = x^T @ dy[r]: op(A) = x^T with x [M,K] as stored ([K',M'] for this product), op(B[r]) = dy[r]^T with
+            # dy[r] [M,N] as stored ([K',N']); long K' = M -> split-K inside. No transposed copies.
+            dw = gemm(x, dy, trans_a=True, trans_b=True)
         return dx, dw
 
 

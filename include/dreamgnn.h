@@ -167,6 +167,15 @@ DG_API int dg_gemm_nt_f32(const float* A, int64_t lda, int64_t stride_a, const f
                           int64_t stride_b, float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N,
                           int64_t K, int64_t batch, const float* row_scale, int precision, void* workspace,
                           size_t workspace_bytes, dg_stream_t stream);
+/* General form: trans_a != 0 means A is given as [K,M] row-major (lda >= M), trans_b != 0 means B is given as
+ * [K,N] row-major (ldb >= N); the tensor cores read such operands MN-major, so no transposed copy is made.
+ * C = op(A) * op(B)^T with op(A) [M,K], op(B) [N,K]; dg_gemm_nt_f32 is the trans_a = trans_b = 0 case. The weight
+ * gradients dW_r = X^T dY_r (backward of layers.py:220-221, 311) use trans_a = trans_b = 1 on X and dY as stored.
+ * Workspace bound: dg_gemm_nt_workspace_bytes (valid for every orientation). */
+DG_API int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_a, const float* B, int64_t ldb,
+                       int64_t stride_b, int trans_b, float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N,
+                       int64_t K, int64_t batch, const float* row_scale, int precision, void* workspace,
+                       size_t workspace_bytes, dg_stream_t stream);
 
 /* ---- kNN similarity graphs (data_loader.py:278-344, utils.py:11-27) ------------------------- */
 /* Per row of a float64 similarity block [n_rows, n_cols] (leading dimension ld), the k largest

@@ -35,7 +35,21 @@ for (M, N, K, R) in shapes:
         th.cuda.synchronize()
         print('M=%d N=%d K=%d R=%d prec=%d rel err %.3e (torch fp32 %.3e)' % (M, N, K, R, prec, rel(c, ref),
               rel(a @ b.transpose(-1, -2), ref)), flush=True)
+for (M, N, K, R) in [(128, 128, 32, 1), (130, 70, 36, 1), (257, 129, 100, 3), (1024, 344, 5000, 2)]:
+    a = th.randn(M, K, device=dev, generator=g)
+    b = th.randn(R, N, K, device=dev, generator=g) if R > 1 else th.randn(N, K, device=dev, generator=g)
+    ref = a.double() @ b.double().transpose(-1, -2)
+    for ta, tb in ((True, False), (False, True), (True, True)):
+        c = ops.gemm(a.t().contiguous() if ta else a, b.transpose(-1, -2).contiguous() if tb else b, trans_a=ta, trans_b=tb)
+        th.cuda.synchronize()
+        print('M=%d N=%d K=%d R=%d trans_a=%d trans_b=%d rel err %.3e' % (M, N, K, R, ta, tb, rel(c, ref)), flush=True)
 if len(sys.argv) > 1:
+    for (M, N, K, R) in [(1024, 344, 100000, 2), (1024, 768, 100000, 1)]:      # weight gradients: X^T dY as stored
+        x = th.randn(K, M, device=dev, generator=g)
+        dy = th.randn(R, K, N, device=dev, generator=g)
+        t0 = timeit(lambda: ops.gemm(x, dy, trans_a=True, trans_b=True))
+        t1 = timeit(lambda: ops.gemm_nt(x.t(), dy.transpose(1, 2)))
+        print('dW M=%d N=%d K=%d R=%d: MN-major operands %.3f ms, with transposed copies %.3f ms' % (M, N, K, R, t0, t1), flush=True)
     for (M, N, K, R) in [(100000, 344, 1024, 2), (50000, 344, 768, 2), (100000, 768, 1024, 1), (1024, 344, 100000, 2),
                          (1024, 768, 100000, 1)]:
         a = th.randn(M, K, device=dev, generator=g)

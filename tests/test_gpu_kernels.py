@@ -337,6 +337,24 @@ def test_gemm_nt_3xtf32(dev, M, N, K, R):
     assert H.rel_err(tf32.cpu(), ref) <= 2e-3
 
 
+@pytest.mark.parametrize('ta,tb', [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize('M,N,K,R', [(1, 1, 1, 1), (128, 128, 32, 1), (130, 70, 36, 1), (257, 129, 100, 3), (96, 344, 5000, 2),
+                                    (1024, 341, 777, 2)])
+def test_gemm_transposed_operands(dev, M, N, K, R, ta, tb):
+    """op(A) [M,K] / op(B) [N,K] given as [K,M] / [K,N] row-major: read MN-major by the tensor cores (and through the
+    packing copy when a row stride is not a multiple of 16 bytes), same result as the explicit transposes."""
+    gen = th.Generator().manual_seed(M + N + K)
+    a = th.randn(M, K, generator=gen)
+    b = th.randn(R, N, K, generator=gen) if R > 1 else th.randn(N, K, generator=gen)
+    ref = a.double() @ b.double().transpose(-1, -2)
+    a_in = a.t().contiguous() if ta else a
+    b_in = b.transpose(-1, -2).contiguous() if tb else b
+    got = ops().gemm(a_in.to(dev), b_in.to(dev), trans_a=ta, trans_b=tb)
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert H.rel_err(got.cpu(), ref) <= FP32_TOL
+    assert th.equal(got, ops().gemm(a_in.to(dev), b_in.to(dev), trans_a=ta, trans_b=tb))
+
+
 def test_project_autograd_on_tensor_cores(dev):
     o = ops()
     gen = th.Generator().manual_seed(3)
