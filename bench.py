@@ -164,19 +164,18 @@ def run_b200(args):
         aug_params = aug_params_from_args(argparse.Namespace())
         closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
         step = lambda: train_iteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
-        eager_log, eager_launches = None, 0
+        eager_step, eager_launches = step, 0
         if args.cuda_graph:
-            # kernels replayed from a graph are invisible to the Python-side launch log and counter: take both
-            # from one eager step of the identical iteration (same kernels, same shapes) before capturing
+            # kernels replayed from a graph are invisible to the C-ABI launch counter: count one eager step of the
+            # identical iteration (same kernels, same shapes) before capturing
             from dreamgnn_b200.graphed import GraphedIteration
             for _ in range(2):
                 step()
             th.cuda.synchronize()
-            ops.PROFILE = []
             _lib.reset_launch_count()
             step()
             th.cuda.synchronize()
-            eager_log, eager_launches, ops.PROFILE = ops.PROFILE, _lib.launch_count(), None
+            eager_launches = _lib.launch_count()
             step = GraphedIteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
     del w
 
@@ -202,6 +201,8 @@ def run_b200(args):
     barrier()
 
     # ---- timed region: exactly K steps, device-timed, SpMM launches logged with events -------------
+    import gc
+    gc.collect()
     sampler = ClockSampler(local)
     sampler.start()
     ops.PROFILE = []
@@ -238,8 +239,18 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count()
     log, ops.PROFILE = ops.PROFILE, None
+    log_steps = args.steps
     if args.cuda_graph and not rows:
-        log, launches = eager_log * args.steps, eager_launches * args.steps
+        # the graph replays carry no per-kernel events: the per-launch SpMM durations behind `roofline` come from
+        # eager steps of the same iteration run right here (CUDA events around every SpMM launch on its stream),
+        # while the clock sampler is still running
+        launches = eager_launches * args.steps
+        log_steps = min(3, args.steps)
+        ops.PROFILE = []
+        for _ in range(log_steps):
+            eager_step()
+        th.cuda.synchronize()
+        log, ops.PROFILE = ops.PROFILE, None
     clocks = sampler.stop()
     t = th.tensor([ms], device=dev)
     if world > 1:
@@ -264,22 +275,31 @@ def run_b200(args):
             ev.record(copy_stream)
         return bufs, ev
 
+    def e2e_steps(n):
+        nxt = upload()
+        last = None
+        for i in range(n):
+            bufs, ev = nxt
+            th.cuda.current_stream().wait_event(ev)
+            for k, v in bufs.items():
+                v.record_stream(th.cuda.current_stream())
+                if args.cuda_graph and not rows:
+                    getattr(state, k).copy_(v)        # the captured graph reads its own static input buffers
+                else:
+                    setattr(state, k, v)
+            if sim_is_feat and not (args.cuda_graph and not rows):
+                state.drug_sim_feat, state.dis_sim_feat = state.drug_feat, state.dis_feat
+            if rows:
+                state.dec.labels = state.labels
+            if i + 1 < n:
+                nxt = upload()                                            # prefetch the next step's inputs
+            last = float(step().item())                                   # D2H read of the step's result
+        return last
+
+    e2e_steps(3)            # untimed: the upload buffers enter the allocator's pool (a cudaMalloc mid-loop stalls the device)
     barrier()
     e0.record()
-    nxt = upload()
-    for i in range(args.steps):
-        bufs, ev = nxt
-        th.cuda.current_stream().wait_event(ev)
-        for k, v in bufs.items():
-            v.record_stream(th.cuda.current_stream())
-            setattr(state, k, v)
-        if sim_is_feat:
-            state.drug_sim_feat, state.dis_sim_feat = state.drug_feat, state.dis_feat
-        if rows:
-            state.dec.labels = state.labels
-        if i + 1 < args.steps:
-            nxt = upload()                                                # prefetch the next step's inputs
-        loss_host = float(step().item())                                  # D2H read of the step's result
+    loss_host = e2e_steps(args.steps)
     e1.record()
     barrier()
     t = th.tensor([e0.elapsed_time(e1)], device=dev)
@@ -288,7 +308,7 @@ def run_b200(args):
     ms_e2e = float(t.item())
 
     # ---- metric ---------------------------------------------------------------------------------
-    agg_edges = sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / args.steps
+    agg_edges = sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / log_steps
     it_s = args.steps / (ms_max / 1e3)
     if rows:                                                          # one job: edges are summed over ranks
         t = th.tensor([agg_edges], device=dev, dtype=th.float64)
@@ -309,9 +329,9 @@ def run_b200(args):
         c['bmin'] += spmm_compulsory_bytes(nnz, nr, nc, d, el, valued)
         c['n'] += 1
         c['nnz'] += nnz
-    per_step = len(log) // max(args.steps, 1)
+    per_step = len(log) // max(log_steps, 1)
     spmm_ms_by_step = [round(sum(r[7].elapsed_time(r[8]) for r in log[i * per_step:(i + 1) * per_step]), 2)
-                       for i in range(args.steps)] if per_step else []
+                       for i in range(log_steps)] if per_step else []
     top_key, top = max(classes.items(), key=lambda kv: kv[1]['ms'])
     peak, peak_src = measured_peak()
     achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
@@ -327,8 +347,10 @@ def run_b200(args):
                 'algorithmic_bytes_per_launch': int(top['bytes'] / top['n']),
                 'model': 'gather: nnz*(4[+4]+d*s) + n_rows*d*4 + index/scale vectors (SURVEY 8d)',
                 'compulsory_frac': round(top['bmin'] / (top['ms'] / 1e3) / 1e9 / peak, 4),
-                'share_of_step': round(top['ms'] / ms, 4),
-                'all_spmm_classes': {'%s_d%d_b%d' % k: {'ms_per_step': round(v['ms'] / args.steps, 3),
+                'share_of_step': round(top['ms'] / log_steps / (ms / args.steps), 4),
+                'timed_in': ('%d eager steps of the same iteration run after the graph-replayed timed region' % log_steps)
+                            if (args.cuda_graph and not rows) else 'the timed region',
+                'all_spmm_classes': {'%s_d%d_b%d' % k: {'ms_per_step': round(v['ms'] / log_steps, 3),
                                                         'GBps': round(v['bytes'] / (v['ms'] / 1e3) / 1e9, 1),
                                                         'GEps': round(v['nnz'] / (v['ms'] / 1e3) / 1e9, 2)}
                                      for k, v in classes.items()}}
@@ -359,8 +381,10 @@ def run_b200(args):
            'e2e': {'value': round(e2e_value, 4), 'unit': 'GE/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
                    'what': 'features + labels copied from pinned host memory every step (next step prefetched on a side '
-                           'stream while the current one computes), loss read back every step; graph structure stays '
-                           'resident as in the reference training loop (train.py:186-200)'},
+                           'stream while the current one computes%s), loss read back every step; graph structure stays '
+                           'resident as in the reference training loop (train.py:186-200)'
+                           % (', then copied device-to-device into the captured graph\'s input buffers'
+                              if (args.cuda_graph and not rows) else '')},
            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'step_ms': step_ms, 'allocator': alloc_diag, 'host_enqueue_ms': host_ms, 'spmm_ms_by_step': spmm_ms_by_step,
            'final_loss': round(loss_host, 6)}
 
@@ -506,6 +530,7 @@ def main():
     ap.add_argument('--scale', type=float, default=1.0, help='proportional shrink of the workload (tests)')
     ap.add_argument('--cpu-scale', type=float, default=0.0, help='scale of the CPU sample (default: scale/40 for syn*)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='per-kernel launches instead of one CUDA-graph replay per step')
     ap.add_argument('--cuda-graph', action='store_true',
                     help='replay the whole training iteration from one captured CUDA graph (launch-bound small shapes)')
     ap.add_argument('--messages', default='f32', choices=['f32', 'bf16'],
@@ -513,6 +538,13 @@ def main():
     ap.add_argument('--parallel', default='folds', choices=['folds', 'rows'],
                     help='N>1: independent fold-replicas (weak scaling, default) or one row-partitioned graph (strong)')
     args = ap.parse_args()
+    # default launch mode: one CUDA-graph replay per step for the single-graph-per-GPU workloads (the eager host loop
+    # enqueues ~800 launches per step at ~85 % of the device time and any host hiccup starves the GPU: measured
+    # random 100-300 ms steps); --eager keeps per-kernel launches. The row-partitioned path (NCCL inside) stays eager.
+    if args.parallel == 'rows' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        args.cuda_graph = False
+    elif not args.eager:
+        args.cuda_graph = True
     if args.impl == 'reference':
         run_reference(args)
     else:

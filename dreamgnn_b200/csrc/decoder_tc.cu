@@ -7,8 +7,8 @@
 // off the critical path:
 //
 //   forward   z2 tile [128 pairs x 64]  = z1 [128 x 128] . W2^T            (A, B K-major)
-//   backward  dz1 tile [64 pairs x 128] = dz2 [64 x 64] . W2               (A K-major padded to M=128, B = W2 as
-//                                                                            stored, i.e. MN-major)
+//   backward  dz1^T tile [128 x 64 pairs] = W2^T [128 x 64] . dz2^T          (A = W2^T, B = dz2, both K-major; the
+//                                                                            transposed product fills all 128 rows)
 //             dW2^T [128 x 64]         += z1^T . dz2  over the tile's pairs (A and B MN-major: pairs are K)
 //
 // The operand tiles are written by the gathering threads straight into the swizzled layouts the UMMA
@@ -88,27 +88,36 @@ __device__ __forceinline__ void stage_w2(const float* __restrict__ w2, uint8_t* 
 
 // Gather of z1 = drop(relu(pd[src] + ps[dst])) for one tile, software-pipelined through registers: a warp owns
 // U consecutive pairs of the tile, a lane 4 consecutive hidden-1 units of each (one float4 per operand row).
-// `issue` starts the row loads of a tile (2 * U float4 in flight per lane, 512 threads: 64 KB per SM at U = 4);
-// `commit` -- called one tile later, after the previous tile's MMAs have retired -- finishes z1 and writes the
+// `issue_idx` loads a tile's endpoints, `issue_rows` -- one tile later -- starts its row loads (2 * U float4 in flight
+// per lane, 512 threads: 64 KB per SM at U = 4), `commit` -- another tile later, after the previous tile's MMAs have
+// retired -- finishes z1 and writes the
 // hi / lo halves into the swizzled operand tiles: 4 blocks of 32 units, each [kTile pairs][128 B], K-major for
 // the forward GEMM, MN-major (pairs are K) for the backward dW2 GEMM.
 template <int U>
 struct GatherRegs {
   float4 a[U], b[U];
-};
+  int s, d;                // lane u < U: endpoints of pair u of the tile after the one in a / b (the index loads run two
+};                         // tiles ahead, so the row loads never wait on them); -1 past the end
 
 template <int U>
-__device__ __forceinline__ void gather_issue(const int* __restrict__ src, const int* __restrict__ dst, int64_t base,
-                                             int64_t n_pairs, const float* __restrict__ pd, const float* __restrict__ ps,
-                                             GatherRegs<U>& r) {
+__device__ __forceinline__ void gather_issue_idx(const int* __restrict__ src, const int* __restrict__ dst, int64_t base,
+                                                 int64_t n_pairs, GatherRegs<U>& r) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e = base + warp * U + lane;
+  r.s = -1;
+  r.d = -1;
+  if (lane < U && e < n_pairs) { r.s = __ldg(src + e); r.d = __ldg(dst + e); }
+}
+
+template <int U>
+__device__ __forceinline__ void gather_issue_rows(const float* __restrict__ pd, const float* __restrict__ ps, GatherRegs<U>& r) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int64_t e = base + warp * U + u;
-    if (e < n_pairs) {
-      const int s = __ldg(src + e), d = __ldg(dst + e);
-      r.a[u] = __ldg(reinterpret_cast<const float4*>(pd + static_cast<int64_t>(s) * H1) + lane);
-      r.b[u] = __ldg(reinterpret_cast<const float4*>(ps + static_cast<int64_t>(d) * H1) + lane);
+    const int su = __shfl_sync(kFull, r.s, u), du = __shfl_sync(kFull, r.d, u);
+    if (su >= 0) {
+      r.a[u] = __ldg(reinterpret_cast<const float4*>(pd + static_cast<int64_t>(su) * H1) + lane);
+      r.b[u] = __ldg(reinterpret_cast<const float4*>(ps + static_cast<int64_t>(du) * H1) + lane);
     } else {
       r.a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       r.b[u] = r.a[u];
@@ -167,7 +176,9 @@ decoder_fwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
   constexpr int U = kFT / (kTcThreads / 32);         // pairs per warp
   if (drop.seed_dev) drop.seed = *drop.seed_dev;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the swizzle atoms, kept as an offset from the __shared__ array so that the compiler
+  // still knows the address space (LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* A_hi = smem;
   uint8_t* A_lo = A_hi + 4 * kFBlk;                  // (kFT = 64: the M=128 descriptors over-read into what follows --
   uint8_t* W_hi = A_lo + 4 * kFBlk;                  //  finite values whose accumulator rows 64..127 are never read)
@@ -201,7 +212,9 @@ decoder_fwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
   const int64_t n_tiles = (n_pairs + kFT - 1) / kFT;
   GatherRegs<U> regs;
   int64_t tile = blockIdx.x;
-  if (tile < n_tiles) gather_issue<U>(src, dst, tile * kFT, n_pairs, pd, ps, regs);
+  gather_issue_idx<U>(src, dst, tile * kFT, n_pairs, regs);               // (past-the-end tiles load nothing)
+  gather_issue_rows<U>(pd, ps, regs);
+  gather_issue_idx<U>(src, dst, (tile + gridDim.x) * kFT, n_pairs, regs);
   for (; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kFT;
     gather_commit<kFT, U, false>(regs, base, drop, A_hi, A_lo);
@@ -222,8 +235,9 @@ decoder_fwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
       }
       umma_commit(bar_a);
     }
-    // next tile's rows: in flight while the tensor core and the epilogue work on this one
-    if (tile + gridDim.x < n_tiles) gather_issue<U>(src, dst, (tile + gridDim.x) * kFT, n_pairs, pd, ps, regs);
+    // next tile's rows (and the endpoints of the one after): in flight while the tensor core and the epilogue work
+    gather_issue_rows<U>(pd, ps, regs);
+    gather_issue_idx<U>(src, dst, (tile + 2 * static_cast<int64_t>(gridDim.x)) * kFT, n_pairs, regs);
     mbar_wait(bar_a, phase);
     phase ^= 1;
     tc_fence_after();
@@ -290,10 +304,11 @@ decoder_fwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
 // ------------------------------------------------------------------------------------------------
 constexpr int kBT = 64;
 constexpr int kBBlk = kBT * 128;                     // 8 KB: [64 pairs][32 columns]
-constexpr int kBwdTmemCols = 256;                    // D1 (dz1) columns 0..127, D2 (dW2^T) columns 128..191
+constexpr int kBwdTmemCols = 128;                    // D1 (dz1^T: units x pairs) columns 0..63, D2 (dW2^T: units x j) 64..127
+constexpr int kWtBlk = H1 * 128;                     // 16 KB: W2^T block [128 units][32 j]
 constexpr int kFlushTiles = 4;                       // K = 256 pairs per TMEM accumulation of dW2 (truncation bias, see above)
-constexpr size_t kBwdTcSmem = 1024 + 8 * kBBlk /*z1 hi,lo*/ + 8 * kBBlk /*dz2 hi,lo in both layouts*/ + 8 * kWBlk + 64;
-constexpr uint32_t kIdescDz1 = tf32_idesc(128, H1, 0, 1);     // A = dz2 K-major, B = W2 MN-major
+constexpr size_t kBwdTcSmem = 1024 + 8 * kBBlk /*z1 hi,lo*/ + 8 * kBBlk /*dz2 hi,lo in both layouts*/ + 4 * kWtBlk + 64;
+constexpr uint32_t kIdescDz1 = tf32_idesc(128, kBT, 0, 0);    // A = W2^T, B = dz2, both K-major (K = j)
 constexpr uint32_t kIdescDw2 = tf32_idesc(128, H2, 1, 1);     // A = z1 MN-major, B = dz2 MN-major
 constexpr int kPairGroups = kTcThreads / 16;         // 32 pair groups x 16 column groups in the dz2 phase
 constexpr int kPP = kBT / kPairGroups;               // 2 pairs per thread
@@ -306,20 +321,34 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
                       const float* __restrict__ dout, float* __restrict__ dz1, float* __restrict__ partials) {
   if (drop.seed_dev) drop.seed = *drop.seed_dev;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the swizzle atoms, kept as an offset from the __shared__ array so that the compiler
+  // still knows the address space (LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* Z_hi = smem;                              // 4 blocks [64 pairs][32 units], MN-major (pairs are K)
   uint8_t* Z_lo = Z_hi + 4 * kBBlk;
-  uint8_t* DZ_hi = Z_lo + 4 * kBBlk;                 // 2 blocks [64 pairs][32 hidden-2 units], K-major (A of the dz1 GEMM;
-  uint8_t* DZ_lo = DZ_hi + 2 * kBBlk;                //  its M=128 descriptors over-read into what follows: finite values
-  uint8_t* DM_hi = DZ_lo + 2 * kBBlk;                //  whose accumulator rows 64..127 are never read)
-  uint8_t* DM_lo = DM_hi + 2 * kBBlk;                // the same dz2 tile MN-major (B of the dW2 GEMM)
-  uint8_t* W_hi = DM_lo + 2 * kBBlk;                 // W2 image, MN-major (N = unit, K = j)
-  uint8_t* W_lo = W_hi + 4 * kWBlk;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(W_lo + 4 * kWBlk);
+  uint8_t* DZ_hi = Z_lo + 4 * kBBlk;                 // 2 blocks [64 pairs][32 hidden-2 units], K-major (B of the dz1 GEMM)
+  uint8_t* DZ_lo = DZ_hi + 2 * kBBlk;
+  uint8_t* DM_hi = DZ_lo + 2 * kBBlk;                // the same dz2 tile MN-major (B of the dW2 GEMM)
+  uint8_t* DM_lo = DM_hi + 2 * kBBlk;
+  uint8_t* W_hi = DM_lo + 2 * kBBlk;                 // W2^T image: 2 blocks [128 units][32 j], K-major (A of the dz1 GEMM)
+  uint8_t* W_lo = W_hi + 2 * kWtBlk;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(W_lo + 2 * kWtBlk);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
-  stage_w2<true>(w2, W_hi, W_lo);
+  for (int i = t; i < H2 * H1 / 4; i += kTcThreads) {      // w2 [j][unit] row-major -> W2^T rows = units, K = j contiguous
+    const int j = i >> 5, u0 = (i & 31) * 4;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(w2) + i);
+    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t off = static_cast<uint32_t>(j >> 5) * kWtBlk + sw128_off(u0 + r, (j & 31) >> 2) + (j & 3) * 4;
+      float hi, lo;
+      split_tf32(xv[r], hi, lo);
+      *reinterpret_cast<float*>(W_hi + off) = hi;
+      *reinterpret_cast<float*>(W_lo + off) = lo;
+    }
+  }
   const uint32_t bar1 = smem_u32(bars), bar2 = smem_u32(bars + 1);
   if (t == 0) {
     mbar_init(bar1, 1);
@@ -332,7 +361,7 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + 128;
+  const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + kBT;
 
   // dz2 phase role: pairs pz .. pz+kPP-1, hidden-2 units jz .. jz+3
   const int pz = (t >> 4) * kPP, jz = (t & 15) * 4;
@@ -376,10 +405,10 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
   const int64_t n_tiles = (n_pairs + kBT - 1) / kBT;
   GatherRegs<kBU> regs;
   int64_t tile = blockIdx.x;
-  if (tile < n_tiles) {
-    issue_z2(tile * kBT);
-    gather_issue<kBU>(src, dst, tile * kBT, n_pairs, pd, ps, regs);
-  }
+  issue_z2(tile * kBT);                                                    // (past-the-end tiles load nothing)
+  gather_issue_idx<kBU>(src, dst, tile * kBT, n_pairs, regs);
+  gather_issue_rows<kBU>(pd, ps, regs);
+  gather_issue_idx<kBU>(src, dst, (tile + gridDim.x) * kBT, n_pairs, regs);
   for (; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t base = tile * kBT;
     gather_commit<kBT, kBU, true>(regs, base, drop, Z_hi, Z_lo);
@@ -407,14 +436,12 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
     __syncthreads();
     if (t == 0) {
       tc_fence_after();
-      // dz1 [pairs x units] = dz2 [pairs x j] . W2 [j x units]: K = 64 j in 8 slices
+      // dz1^T [units x pairs] = W2^T [units x j] . dz2^T [j x pairs]: K = 64 j in 8 slices of 32 bytes along the rows
 #pragma unroll
       for (int s = 0; s < 8; ++s) {
-        const uint32_t a_off = (s >> 2) * kBBlk + (s & 3) * 32;          // K-major: +32 B per slice inside a block
-        const uint32_t b_off = s * 1024;                                 // MN-major: next 8 K-rows (j)
-        mma3(tmem_d1, smem_desc_sw128(smem_u32(DZ_hi + a_off)), smem_desc_sw128(smem_u32(DZ_lo + a_off)),
-             smem_desc_mn32(smem_u32(W_hi + b_off), kWBlk, 512), smem_desc_mn32(smem_u32(W_lo + b_off), kWBlk, 512),
-             kIdescDz1, s ? 1u : 0u);
+        const uint32_t a_off = (s >> 2) * kWtBlk + (s & 3) * 32, b_off = (s >> 2) * kBBlk + (s & 3) * 32;
+        mma3(tmem_d1, smem_desc_sw128(smem_u32(W_hi + a_off)), smem_desc_sw128(smem_u32(W_lo + a_off)),
+             smem_desc_sw128(smem_u32(DZ_hi + b_off)), smem_desc_sw128(smem_u32(DZ_lo + b_off)), kIdescDz1, s ? 1u : 0u);
       }
       umma_commit(bar1);
       // dW2^T [units x j] += z1^T [units x pairs] . dz2 [pairs x j]: K = 64 pairs in 8 slices
@@ -427,29 +454,27 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
       }
       umma_commit(bar2);
     }
-    // next tile's rows / z2 / dout: in flight while the tensor core and the epilogue work on this one
-    if (tile + gridDim.x < n_tiles) {
-      issue_z2((tile + gridDim.x) * kBT);
-      gather_issue<kBU>(src, dst, (tile + gridDim.x) * kBT, n_pairs, pd, ps, regs);
-    }
-    // ---- dz1 epilogue: rows 0..63 of D1 = lanes of warps with q < 2; columns 32g .. +31 = unit block g ----
+    // next tile's rows / z2 / dout (and the endpoints of the tile after): in flight while the tensor core and the
+    // epilogue work on this one
+    issue_z2((tile + gridDim.x) * kBT);
+    gather_issue_rows<kBU>(pd, ps, regs);
+    gather_issue_idx<kBU>(src, dst, (tile + 2 * static_cast<int64_t>(gridDim.x)) * kBT, n_pairs, regs);
+    // ---- dz1 epilogue: this thread holds unit 32q + lane of pairs 16g .. 16g+15; a warp stores 128 contiguous
+    // bytes of one pair's row per instruction ----
     mbar_wait(bar1, it & 1);
     tc_fence_after();
-    if (q < 2) {
-      uint32_t v[32];
-      tmem_ld32(tmem_d1 + (static_cast<uint32_t>(q * 32) << 16) + g * 32, v);
+    {
+      uint32_t v[16];
+      tmem_ld16(tmem_d1 + (static_cast<uint32_t>(q * 32) << 16) + g * 16, v);
       tmem_ld_wait();
-      const int p = q * 32 + lane;
-      const int64_t e = base + p;
-      if (e < n_pairs) {
-        const float s = drop.scale;
+      const float sc = drop.scale;
+      const uint8_t* zrow = Z_hi + q * kBBlk + (lane & 7) * 4;             // unit 32q + lane: 32-byte chunk lane >> 3
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 z = *reinterpret_cast<const float4*>(Z_hi + g * kBBlk + mn32_off(p, c));
-          __stcs(reinterpret_cast<float4*>(dz1 + e * H1 + g * 32 + c * 4),
-                 make_float4(z.x > 0.f ? __uint_as_float(v[c * 4]) * s : 0.f, z.y > 0.f ? __uint_as_float(v[c * 4 + 1]) * s : 0.f,
-                             z.z > 0.f ? __uint_as_float(v[c * 4 + 2]) * s : 0.f, z.w > 0.f ? __uint_as_float(v[c * 4 + 3]) * s : 0.f));
-        }
+      for (int j = 0; j < 16; ++j) {
+        const int p = g * 16 + j;
+        const int64_t e = base + p;
+        const float z = *reinterpret_cast<const float*>(zrow + p * 128 + (((lane >> 3) ^ (p & 3)) << 5));
+        if (e < n_pairs) __stcs(dz1 + e * H1 + q * 32 + lane, z > 0.f ? __uint_as_float(v[j]) * sc : 0.f);
       }
     }
     mbar_wait(bar2, it & 1);                             // z1 / dz2 tiles free again

@@ -54,7 +54,8 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int kStages = kSplit3 ? 3 : 6;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the dynamic window is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (kept as an offset from the __shared__ array so the transform warps get LDS / STS rather than generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // barriers: full[kStages] (TMA landed), empty[kStages] (MMAs retired), ready[kStages] (hi/lo written), tmem_full
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
