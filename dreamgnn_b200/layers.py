@@ -218,7 +218,7 @@ class GCMCLayer(nn.Module):
             out[dst_type] = agg[:, :D] if dp != D else agg
         drug = self.dropout(self.agg_act(out['drug']))
         dis = self.dropout(self.agg_act(out['disease']))
-        return self.ifc(drug), self.ufc(dis)
+        return (ops.linear(drug, self.ifc.weight, self.ifc.bias), ops.linear(dis, self.ufc.weight, self.ufc.bias))
 
 
 class GraphConvolution(nn.Module):
@@ -316,8 +316,9 @@ class FGCN(nn.Module):
         else:
             emb1_sim, emb1_feat = self.FGCN_drug.forward_shared(drug_sim_feat, [drug_graph, drug_feature_graph])
             emb2_sim, emb2_feat = self.FGCN_disease.forward_shared(disease_sim_feat, [dis_graph, disease_feature_graph])
-        fused_drug = th.relu(self.drug_fusion(th.cat([emb1_sim, emb1_feat], dim=1)))
-        fused_disease = th.relu(self.disease_fusion(th.cat([emb2_sim, emb2_feat], dim=1)))
+        fused_drug = th.relu(ops.linear(th.cat([emb1_sim, emb1_feat], dim=1), self.drug_fusion.weight, self.drug_fusion.bias))
+        fused_disease = th.relu(ops.linear(th.cat([emb2_sim, emb2_feat], dim=1), self.disease_fusion.weight,
+                                           self.disease_fusion.bias))
         emb1 = F.dropout(fused_drug, p=self.dropout, training=self.training)
         emb2 = F.dropout(fused_disease, p=self.dropout, training=self.training)
         return emb1, emb2, emb1_sim, emb1_feat, emb2_sim, emb2_feat
@@ -356,8 +357,8 @@ class MLPDecoder(nn.Module):
     def forward(self, graph, drug_feat, dis_feat):
         n_in = drug_feat.shape[1]
         w1 = self.lin1.weight
-        pd = F.linear(drug_feat, w1[:, :n_in], self.lin1.bias)     # drug half of lin1 (+ bias)
-        ps = F.linear(dis_feat, w1[:, n_in:])                      # disease half
+        pd = ops.linear(drug_feat, w1[:, :n_in], self.lin1.bias)   # drug half of lin1 (+ bias)
+        ps = ops.linear(dis_feat, w1[:, n_in:])                    # disease half
         if hasattr(graph, 'partition'):                            # this rank's slice of the pairs; node rows gathered
             from . import dist as _dist
             pairs, pd, ps = graph.pairs, _dist.all_gather_rows(pd), _dist.all_gather_rows(ps)

@@ -460,6 +460,39 @@ class ProjectFunction(th.autograd.Function):
         return dx, dw
 
 
+class LinearFunction(th.autograd.Function):
+    """y = x @ w^T + b (nn.Linear) with the three GEMMs on the tensor cores: both forward operands are K-major as
+    stored; dx = dy @ w reads w as stored ([K',N']); dw = dy^T @ x reads dy and x as stored ([K',M'], [K',N'])."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        y = gemm_nt(x, w)
+        if b is not None:
+            y += b
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = gemm(dy, w, trans_b=True) if ctx.needs_input_grad[0] else None
+        dw = gemm(dy, x, trans_a=True, trans_b=True) if ctx.needs_input_grad[1] else None
+        db = dy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def linear(x, w, b=None):
+    """F.linear(x, w, b) for 2-D x; tcgen05 3xTF32 above GEMM_MIN_MACS, cuBLAS (torch) below."""
+    if not x.is_cuda:
+        raise RuntimeError('dreamgnn_b200.linear needs CUDA tensors (no CPU fallback)')
+    if (gemm_backend() == 'tcgen05' and x.dim() == 2 and x.dtype == th.float32 and w.dtype == th.float32
+            and x.shape[0] * w.shape[0] * w.shape[1] >= GEMM_MIN_MACS):
+        return LinearFunction.apply(x, w, b)
+    return th.nn.functional.linear(x, w, b)
+
+
 def project(x, w):
     """x [M,K] @ w [R,K,N] -> [R,M,N]; tcgen05 3xTF32 for the large projections, cuBLAS below GEMM_MIN_MACS."""
     if not x.is_cuda:

@@ -355,6 +355,30 @@ def test_gemm_transposed_operands(dev, M, N, K, R, ta, tb):
     assert th.equal(got, ops().gemm(a_in.to(dev), b_in.to(dev), trans_a=ta, trans_b=tb))
 
 
+@pytest.mark.parametrize('M,K,N,bias', [(700, 341, 128, True), (513, 256, 128, True), (300, 128, 128, False)])
+def test_linear_autograd_on_tensor_cores(dev, M, K, N, bias):
+    """nn.Linear forward / backward through dg_gemm_f32 (unaligned 341-wide rows go through the packing copy)."""
+    o = ops()
+    gen = th.Generator().manual_seed(M + K)
+    x, w, b = th.randn(M, K, generator=gen), th.randn(N, K, generator=gen) * 0.1, th.randn(N, generator=gen)
+    gout = th.randn(M, N, generator=gen)
+    old = o.GEMM_MIN_MACS
+    o.GEMM_MIN_MACS = 0
+    try:
+        xg, wg, bg = (t.to(dev).requires_grad_(True) for t in (x, w, b))
+        y = o.linear(xg, wg, bg if bias else None)
+        y.backward(gout.to(dev))
+    finally:
+        o.GEMM_MIN_MACS = old
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    yr = th.nn.functional.linear(xr, wr, br if bias else None)
+    yr.backward(gout.double())
+    assert H.rel_err(y.detach().cpu(), yr.detach()) <= FP32_TOL
+    assert H.rel_err(xg.grad.cpu(), xr.grad) <= FP32_TOL and H.rel_err(wg.grad.cpu(), wr.grad) <= FP32_TOL
+    if bias:
+        assert H.rel_err(bg.grad.cpu(), br.grad) <= FP32_TOL
+
+
 def test_project_autograd_on_tensor_cores(dev):
     o = ops()
     gen = th.Generator().manual_seed(3)
