@@ -118,6 +118,34 @@ class DrugDataLoader(object):
     def _generate_dec_graph(self, rating_pairs):
         return GB.generate_dec_graph(rating_pairs, self._num_drug, self._num_disease, self._device)
 
+    # data_loader.py:511-582
+    def augment_features(self):
+        """Feature-level augmentation gated by --use_augmentation (noise, masking, optional mix-up)."""
+        if not self.use_augmentation:
+            return self.drug_feature, self.disease_feature
+        from .augmentation import GraphAugmentation as GA
+        p = self.aug_params
+        out = []
+        for feat in (self.drug_feature, self.disease_feature):
+            f = GA.feature_masking(GA.feature_noise(feat.clone(), p.get('feature_noise_scale', 0.05)),
+                                   p.get('feature_mask_rate', 0.1))
+            out.append(GA.mix_up_features(f, p.get('mixup_alpha', 0.2)) if p.get('use_mixup', False) else f)
+        return tuple(out)
+
+    def get_graph_data_for_training(self, cv_idx):
+        cv_data, graphs = self.data_cv[cv_idx], self.cv_specific_graphs[cv_idx]
+        drug_feat, dis_feat = self.augment_features()
+        dev = self._device
+        return {'train_enc_graph': cv_data['train'][0].to(dev), 'train_dec_graph': cv_data['train'][1].to(dev),
+                'train_labels': cv_data['train'][2].to(dev), 'test_enc_graph': cv_data['test'][0].to(dev),
+                'test_dec_graph': cv_data['test'][1].to(dev), 'test_labels': cv_data['test'][2].to(dev),
+                'drug_graph': graphs['drug_graph'].to(dev), 'disease_graph': graphs['disease_graph'].to(dev),
+                'drug_feature_graph': graphs['drug_feature_graph'].to(dev),
+                'disease_feature_graph': graphs['disease_feature_graph'].to(dev),
+                'drug_features': drug_feat.to(dev), 'disease_features': dis_feat.to(dev),
+                'drug_sim_features': th.as_tensor(self.drug_sim_features, dtype=th.float32).to(dev),
+                'disease_sim_features': th.as_tensor(self.disease_sim_features, dtype=th.float32).to(dev)}
+
     @property
     def num_links(self):
         return len(np.unique(self.association_matrix))

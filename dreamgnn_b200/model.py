@@ -48,10 +48,21 @@ class Net(nn.Module):
         """Shared two-view attention (model.py:93-97)."""
         return self.attention(th.stack((topo, feat), dim=1))[0]
 
-    def forward(self, enc_graph, dec_graph, drug_graph, drug_sim_feat, drug_feat, dis_graph, disease_sim_feat,
-                dis_feat, drug_feature_graph=None, disease_feature_graph=None, Two_Stage=False):
+    def embed(self, enc_graph, drug_graph, drug_sim_feat, drug_feat, dis_graph, disease_sim_feat, dis_feat,
+              drug_feature_graph=None, disease_feature_graph=None, Two_Stage=False):
+        """Everything of `forward` up to the decoder: the four route outputs and the two fused node embeddings the
+        decoder scores pairs from (model.py:65-97). Not part of the reference API: `forward` is this + the decoder,
+        and the all-pairs scoring of `predict.get_top_novel_predictions` calls it once instead of once per batch."""
         drug_out, dis_out = self._topology_route(enc_graph, drug_feat, dis_feat, Two_Stage)
         drug_sim_out, dis_sim_out = self.FGCN(drug_graph, drug_sim_feat, dis_graph, disease_sim_feat,
                                               drug_feature_graph, disease_feature_graph)[:2]
-        scores = self.decoder(dec_graph, self._fuse(drug_out, drug_sim_out), self._fuse(dis_out, dis_sim_out))
+        return (drug_out, drug_sim_out, dis_out, dis_sim_out,
+                self._fuse(drug_out, drug_sim_out), self._fuse(dis_out, dis_sim_out))
+
+    def forward(self, enc_graph, dec_graph, drug_graph, drug_sim_feat, drug_feat, dis_graph, disease_sim_feat,
+                dis_feat, drug_feature_graph=None, disease_feature_graph=None, Two_Stage=False):
+        drug_out, drug_sim_out, dis_out, dis_sim_out, drug_emb, dis_emb = self.embed(
+            enc_graph, drug_graph, drug_sim_feat, drug_feat, dis_graph, disease_sim_feat, dis_feat, drug_feature_graph,
+            disease_feature_graph, Two_Stage)
+        scores = self.decoder(dec_graph, drug_emb, dis_emb)
         return scores, drug_out, drug_sim_out, dis_out, dis_sim_out

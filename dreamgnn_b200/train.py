@@ -191,4 +191,11 @@ def train(args, dataset, cv):
         f.write('iter,train_auroc,train_aupr,test_auroc,test_aupr\n')
         f.write('%d,%.4f,%.4f,%.4f,%.4f\n' % (best['it'], best['train_auroc'], best['train_aupr'], best['auroc'],
                                                 best['aupr']))
+    if getattr(args, 'save_model', False) and getattr(args, 'generate_top_predictions', False):
+        # train.py:369-395: reload the best checkpoint and export the top-K novel pairs
+        from .predict import get_top_novel_predictions
+        best_model = Net(args=args).to(dev)
+        best_model.load_state_dict(th.load(os.path.join(args.save_dir, 'best_model_fold%s.pth' % args.save_id)))
+        top = get_top_novel_predictions(args, best_model, dataset, cv, top_k=args.top_k)
+        print('Top 5 novel predictions:\n%s' % top.head(5))
     return best['auroc'], best['aupr']

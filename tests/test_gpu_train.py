@@ -91,6 +91,46 @@ def test_train_runs_and_evaluates(loaded):
     feats = (inp['drug_feat'], inp['dis_feat'], inp['drug_sim_feat'], inp['dis_sim_feat'])
     ra, rp = R.evaluate_auc(H.params(g), inp['enc_graph'], inp['dec_pairs'], g['test.labels'], knn, feats, dict(layers=3))
     assert abs(a - ra) <= 1e-3 and abs(p - rp) <= 1e-3
+    # the device metric code equals the reference's sklearn path on the same logits
+    os.environ['DG_EVAL'] = 'sklearn'
+    try:
+        a_sk, p_sk, (y_score, y_true) = evaluate(args, net, {'test': ds.data_cv[0]['test']}, gr['drug_graph'], ds.drug_feature,
+                                                 dsim, gr['disease_graph'], ds.disease_feature, ssim, gr['drug_feature_graph'],
+                                                 gr['disease_feature_graph'], return_predictions=True)
+    finally:
+        del os.environ['DG_EVAL']
+    assert abs(a - a_sk) <= 1e-12 and abs(p - p_sk) <= 1e-12 and y_score.shape == y_true.shape
+
+
+def test_top_novel_predictions(loaded):
+    """predict.get_top_novel_predictions (one encoder pass + one fused decoder launch over all unknown pairs) against the
+    reference's algorithm: the oracle's Net.forward on the same pairs, sigmoid, sort (train.py:26-151)."""
+    from oracle import restate as R
+    from dreamgnn_b200.model import Net
+    from dreamgnn_b200.predict import get_top_novel_predictions, novel_pair_scores
+    root, g, ds = loaded
+    margs = argparse.Namespace(model_activation='leaky', gcn_agg_accum='sum', share_param=True, device=None, dropout=0.3,
+                               attention_dropout=0.1, rating_vals=[0, 1], layers=3, gcn_agg_units=105, gcn_out_units=16,
+                               nhid1=40, nhid2=16, src_in_units=48, dst_in_units=48, fdim_drug=60, fdim_disease=45)
+    net = Net(margs)
+    net.load_state_dict({k[3:]: th.tensor(v) for k, v in g.items() if k.startswith('sd.')})
+    net = net.to('cuda:0')
+    args = argparse.Namespace(device='cuda:0', save_dir=root)
+    drug_id, dis_id, score = novel_pair_scores(args, net, ds, 0)
+    truth = np.asarray(ds.association_matrix)
+    want = np.argwhere(truth == 0)
+    np.testing.assert_array_equal(np.stack([drug_id.cpu().numpy(), dis_id.cpu().numpy()], 1), want)      # order of the nested loops
+    inp = H.net_inputs(g, 'train')
+    inp['dec_pairs'] = (want[:, 0], want[:, 1])
+    ref = th.sigmoid(R.net_forward(H.params(g), **inp, layers=3)[0].reshape(-1)).detach()
+    assert H.rel_err(score.cpu(), ref) <= 1e-5
+    df = get_top_novel_predictions(args, net, ds, 0, top_k=50)
+    assert list(df.columns) == ['drug_id', 'disease_id', 'score', 'drug_name'] and len(df) == 50
+    assert os.path.isfile(os.path.join(root, 'top50_novel_predictions_fold1.csv'))
+    order = th.argsort(ref, descending=True)[:50]
+    assert set(zip(df.drug_id, df.disease_id)) == set(map(tuple, want[order.numpy()]))
+    assert np.all(np.diff(df.score.values) <= 0) and df.drug_name[0] == 'DB%05d' % df.drug_id[0]
+    np.testing.assert_allclose(df.score.values, ref[order].numpy(), rtol=1e-5)
 
 
 def test_cuda_graph_iteration(loaded):
