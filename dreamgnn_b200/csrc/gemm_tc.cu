@@ -29,8 +29,11 @@ namespace dg {
 
 constexpr int kBM = 128, kBN = 128, kBK = 32;            // tile; 32 fp32 = one 128-byte swizzle row
 constexpr int kTileBytes = kBM * kBK * 4;                // 16 KB per operand tile
-constexpr int kGemmThreads = 320;                        // warp 0 TMA, 1 MMA + TMEM, 2..5 epilogue, 6..9 hi/lo transform
-constexpr int kTmemCols = 128;
+constexpr int kXformWarps = 16;                          // warps 2 .. 17 write the lo halves of every stage
+constexpr int kGemmThreads = 64 + 32 * kXformWarps;      // warp 0 TMA, 1 MMA + TMEM, 2..5 also run the epilogue
+// kMT = M sub-tiles (accumulators) per CTA: with 2 the CTA owns a 256 x 128 output tile, so a B tile is fetched once
+// per 256 rows -- the 128 x 128 kernel is bound by the L2 -> SM operand traffic (1 MB of panels per 12 us tile, ~12 TB/s
+// over the chip), not by the tensor pipe or HBM
 
 // instruction descriptor: D = f32 (bits 4-5 = 1), A/B = tf32 (2 at bits 7-9 / 10-12), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28
@@ -45,13 +48,15 @@ struct GemmParams {
   int a_mn, b_mn;          // operand stored [K, M] / [K, N] (MN-major) instead of [M, K] / [N, K]
 };
 
-template <bool kSplit3>
+template <bool kSplit3, int kMT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
-  constexpr int kTiles = kSplit3 ? 4 : 2;                        // tiles per stage
-  constexpr int kStageBytes = kTiles * kTileBytes;
-  constexpr int kStages = kSplit3 ? 3 : 6;
+  constexpr int kABytes = kMT * kTileBytes;                      // A tile: kMT * 128 rows
+  constexpr int kBOff = (kSplit3 ? 2 : 1) * kABytes;             // stage layout: A_hi [A_lo] B_hi [B_lo]
+  constexpr int kStageBytes = kBOff + (kSplit3 ? 2 : 1) * kTileBytes;
+  constexpr int kStages = 192 * 1024 / kStageBytes > 6 ? 6 : 192 * 1024 / kStageBytes;     // 3 / 2 (3xTF32), 6 / 4 (TF32)
+  constexpr int kTmemCols = 128 * kMT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the dynamic window is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
   // (kept as an offset from the __shared__ array so the transform warps get LDS / STS rather than generic LD / ST)
@@ -64,7 +69,7 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // grid.x walks (n tile, batch) fastest so the CTAs that share one A row-panel are co-resident and the
   // panel is fetched from HBM once (measured before: A re-read ~6x, kernel 65 % DRAM-bound)
   const int batch = blockIdx.x / p.n_tiles;
-  const int m0 = blockIdx.y * kBM, n0 = (blockIdx.x - batch * p.n_tiles) * kBN;
+  const int m0 = blockIdx.y * (kBM * kMT), n0 = (blockIdx.x - batch * p.n_tiles) * kBN;
   const int split = blockIdx.z;
   const int tile_z = batch * p.splits + split;                 // slot in the split-K partial buffer
   const int kb0 = split * p.kb_per_split;
@@ -77,7 +82,7 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
-      mbar_init(ready0 + 8 * s, 8);                              // one arrival per transform warp (warps 2..9)
+      mbar_init(ready0 + 8 * s, kXformWarps);                    // one arrival per transform warp
     }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -95,24 +100,25 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
       const int za = p.a_batched ? batch : 0, zb = p.b_batched ? batch : 0;
+      const uint64_t keep = l2_policy_evict_last();            // both operands are re-read by the CTAs of neighbouring tiles
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStages, round = it / kStages;
         mbar_wait(empty0 + 8 * s, (round & 1) ^ 1);
         const uint32_t dst = smem_u32(smem + s * kStageBytes);
         const uint32_t bar = full0 + 8 * s;
-        mbar_expect_tx(bar, 2 * kTileBytes);
+        mbar_expect_tx(bar, kABytes + kTileBytes);
         const int k = (kb0 + it) * kBK;
         // raw fp32 tiles (they become A_hi / B_hi). K-major: one 32 (k) x 128 (rows) box; MN-major: four 32 (mn) x
         // 32 (k) boxes, one per 32-column block of the tile (4 KB each)
-        const uint32_t dst_b = dst + (kSplit3 ? 2 : 1) * kTileBytes;
-        if (!p.a_mn) tma_load_3d(dst, &tmA, bar, k, m0, za);
+        const uint32_t dst_b = dst + kBOff;
+        if (!p.a_mn) tma_load_3d_hint(dst, &tmA, bar, k, m0, za, keep);                // one box of 128 * kMT rows
         else
 #pragma unroll
-          for (int i = 0; i < 4; ++i) tma_load_3d(dst + i * (kTileBytes / 4), &tmA, bar, m0 + 32 * i, k, za);
-        if (!p.b_mn) tma_load_3d(dst_b, &tmB, bar, k, n0, zb);
+          for (int i = 0; i < 4 * kMT; ++i) tma_load_3d_hint(dst + i * (kTileBytes / 4), &tmA, bar, m0 + 32 * i, k, za, keep);
+        if (!p.b_mn) tma_load_3d_hint(dst_b, &tmB, bar, k, n0, zb, keep);
         else
 #pragma unroll
-          for (int i = 0; i < 4; ++i) tma_load_3d(dst_b + i * (kTileBytes / 4), &tmB, bar, n0 + 32 * i, k, zb);
+          for (int i = 0; i < 4; ++i) tma_load_3d_hint(dst_b + i * (kTileBytes / 4), &tmB, bar, n0 + 32 * i, k, zb, keep);
       }
     }
   } else if (warp == 1) {
@@ -123,12 +129,12 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait((kSplit3 ? ready0 : full0) + 8 * s, round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t base = smem_u32(smem + s * kStageBytes);
-        const uint32_t base_b = base + (kSplit3 ? 2 : 1) * kTileBytes;
-        // MN-major tiles: 4 blocks of [32 k-rows][128 B] (LBO = 4 KB between blocks, 4-row swizzle atoms 512 B apart)
+        const uint32_t base_b = base + kBOff;
+        // MN-major tiles: blocks of [32 k-rows][128 B] (LBO = 4 KB between blocks, 4-row swizzle atoms 512 B apart)
         const uint64_t a_hi = p.a_mn ? smem_desc_mn32(base, kTileBytes / 4, 512) : smem_desc_sw128(base);
-        const uint64_t a_lo = p.a_mn ? smem_desc_mn32(base + kTileBytes, kTileBytes / 4, 512) : smem_desc_sw128(base + kTileBytes);
+        const uint64_t a_lo = p.a_mn ? smem_desc_mn32(base + kABytes, kTileBytes / 4, 512) : smem_desc_sw128(base + kABytes);
         const uint64_t b_hi = p.b_mn ? smem_desc_mn32(base_b, kTileBytes / 4, 512) : smem_desc_sw128(base_b);
-        const uint64_t b_lo = p.b_mn ? smem_desc_mn32(base + 3 * kTileBytes, kTileBytes / 4, 512) : smem_desc_sw128(base + 3 * kTileBytes);
+        const uint64_t b_lo = p.b_mn ? smem_desc_mn32(base_b + kTileBytes, kTileBytes / 4, 512) : smem_desc_sw128(base_b + kTileBytes);
         // one UMMA consumes K = 8 tf32: 32 bytes along a K-major row (+2 in the address field), 8 rows = 1 KB of an
         // MN-major block (+64)
         const uint32_t ka = p.a_mn ? 64u : 2u, kb = p.b_mn ? 64u : 2u;
@@ -136,13 +142,18 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-          if (kSplit3) {
-            // small terms first, the dominant product last
-            umma_tf32(tmem_base, a_lo + ka * k, b_hi + kb * k, idesc, acc);
-            umma_tf32(tmem_base, a_hi + ka * k, b_lo + kb * k, idesc, 1u);
-            umma_tf32(tmem_base, a_hi + ka * k, b_hi + kb * k, idesc, 1u);
-          } else {
-            umma_tf32(tmem_base, a_hi + ka * k, b_hi + kb * k, idesc, acc);
+#pragma unroll
+          for (int h = 0; h < kMT; ++h) {                       // M sub-tile h: rows 128h .. of the A tile (16 KB further in
+            const uint32_t d = tmem_base + h * 128;             // either layout), accumulator columns 128h ..
+            const uint64_t ah = a_hi + h * (kTileBytes >> 4) + ka * k, al = a_lo + h * (kTileBytes >> 4) + ka * k;
+            if (kSplit3) {
+              // small terms first, the dominant product last
+              umma_tf32(d, al, b_hi + kb * k, idesc, acc);
+              umma_tf32(d, ah, b_lo + kb * k, idesc, 1u);
+              umma_tf32(d, ah, b_hi + kb * k, idesc, 1u);
+            } else {
+              umma_tf32(d, ah, b_hi + kb * k, idesc, acc);
+            }
           }
         }
         umma_commit(empty0 + 8 * s);                            // frees the stage once these MMAs retire
@@ -150,22 +161,23 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       umma_commit(tfull);                                       // accumulator complete
     }
   } else {
-    // ===== warps 2..9: hi/lo transform of every stage; warps 2..5 then run the epilogue =====
+    // ===== warps 2 ..: hi/lo transform of every stage; warps 2..5 then run the epilogue =====
     // The tensor core reads only the top 19 bits of an fp32 operand (tf32 = truncation), so the raw tile IS
     // the hi operand: hi = x & 0xffffe000 implicitly, and lo = x - hi (exact) is written to the neighbouring
-    // tile at the same swizzled position. 32 KB read + 32 KB written per stage by 256 threads.
+    // tile at the same swizzled position.
     if (kSplit3) {
-      const int tt = threadIdx.x - 2 * 32;                      // 0..255
+      const int tt = threadIdx.x - 2 * 32;                      // 0 .. 32 * kXformWarps - 1
       for (int it = 0; it < n_iter; ++it) {
         const int s = it % kStages, round = it / kStages;
         mbar_wait(full0 + 8 * s, round & 1);
         float4* st = reinterpret_cast<float4*>(smem + s * kStageBytes);
 #pragma unroll
-        for (int i = tt; i < 2 * (kTileBytes / 16); i += 256) {
-          // float4 index i: [0,1024) = A tile, [1024,2048) = B tile (which sits two tiles further)
-          const int idx = i < kTileBytes / 16 ? i : i + kTileBytes / 16;
+        for (int i = tt; i < (kABytes + kTileBytes) / 16; i += 32 * kXformWarps) {
+          // float4 index i: [0, kABytes/16) = A tile (lo goes kABytes further), the rest = B tile (lo one tile further)
+          const bool is_a = i < kABytes / 16;
+          const int idx = is_a ? i : i + kABytes / 16;
           const float4 x = st[idx];
-          st[idx + kTileBytes / 16] = make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u),
+          st[idx + (is_a ? kABytes : kTileBytes) / 16] = make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u),
                                                   x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u),
                                                   x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u),
                                                   x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u));
@@ -183,24 +195,21 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tfull, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const int row = m0 + q * 32 + lane;
-    float scale = 1.f;
-    float* out;
-    int64_t ld;
-    if (p.splits > 1) {
-      out = p.partial + (static_cast<int64_t>(tile_z) * p.M + row) * p.N;
-      ld = p.N;
-    } else {
-      out = p.C + batch * p.stride_c + static_cast<int64_t>(row) * p.ldc;
-      ld = p.ldc;
-      if (p.row_scale && row < p.M) scale = p.row_scale[static_cast<int64_t>(batch) * p.M + row];
-    }
-    (void)ld;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int hc = 0; hc < kMT * (kBN / 32); ++hc) {
+      const int h = hc / (kBN / 32), c = hc - h * (kBN / 32);
+      const int row = m0 + h * kBM + q * 32 + lane;
+      float scale = 1.f;
+      float* out;
+      if (p.splits > 1) {
+        out = p.partial + (static_cast<int64_t>(tile_z) * p.M + row) * p.N;
+      } else {
+        out = p.C + batch * p.stride_c + static_cast<int64_t>(row) * p.ldc;
+        if (p.row_scale && row < p.M) scale = p.row_scale[static_cast<int64_t>(batch) * p.M + row];
+      }
       uint32_t v[32];
       if (n_iter > 0) {
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 128 + c * 32;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -289,13 +298,14 @@ static EncodeTiledFn encode_fn() {
 // (rows) x 1, 128-byte swizzle, out-of-bounds -> 0 (ragged M / N / K edges need no special casing)
 // With mn_major the tensor is [batch, k, rows] (rows contiguous): box = 32 (rows) x 32 (k) x 1 in the 128-byte swizzle
 // with a 32-byte atom.
-static int make_map(CUtensorMap* map, const float* base, int rows, int k, int64_t ld, int64_t bstride, int batch, bool mn_major) {
+static int make_map(CUtensorMap* map, const float* base, int rows, int k, int64_t ld, int64_t bstride, int batch, bool mn_major,
+                    int box_rows = kBM) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("gemm: cuTensorMapEncodeTiled not available from the driver"); return DG_ERR_UNSUPPORTED; }
   const int inner = mn_major ? rows : k, outer = mn_major ? k : rows;
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer), static_cast<cuuint64_t>(batch)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(batch > 1 ? bstride : ld * outer) * 4};
-  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(mn_major ? kBK : kBM), 1};
+  cuuint32_t box[3] = {32, static_cast<cuuint32_t>(mn_major ? kBK : box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -309,7 +319,7 @@ static bool tma_addressable(const float* p, int64_t ld, int64_t bstride, int64_t
 }
 
 struct GemmPlan {
-  int kp, nkb, splits, kb_per_split;
+  int kp, nkb, splits, kb_per_split, mt;
   size_t partial_elems;
 };
 
@@ -317,7 +327,10 @@ static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, int64_t batch) {
   GemmPlan g;
   g.kp = static_cast<int>((K + 3) / 4 * 4);
   g.nkb = static_cast<int>((K + kBK - 1) / kBK);
-  const int64_t tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN) * batch;
+  // 256-row CTA tiles unless the padding to a multiple of 256 would waste more than ~15 % of the MMAs
+  const int64_t m128 = (M + 127) / 128 * 128, m256 = (M + 255) / 256 * 256;
+  g.mt = (m256 * 100 <= m128 * 115) ? 2 : 1;
+  const int64_t tiles = ((M + kBM * g.mt - 1) / (kBM * g.mt)) * ((N + kBN - 1) / kBN) * batch;
   int splits = 1;
   if (tiles < kNumSM && g.nkb >= 16) {                      // small output, long K: split K to fill the SMs
     splits = static_cast<int>((2 * kNumSM + tiles - 1) / tiles);
@@ -362,7 +375,7 @@ int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_a, cons
   const int a_copies = (stride_a != 0 && batch > 1) ? static_cast<int>(batch) : 1;
   const int b_copies = (stride_b != 0 && batch > 1) ? static_cast<int>(batch) : 1;
   GemmPlan g = plan_gemm(M, N, K, batch);
-  DG_REQUIRE((M + kBM - 1) / kBM <= 65535 && g.splits <= 65535, "grid too large");
+  DG_REQUIRE((M + kBM * g.mt - 1) / (kBM * g.mt) <= 65535 && g.splits <= 65535, "grid too large");
   const bool split3 = precision == 0;
   Workspace w(workspace, workspace_bytes);
   auto blocks = [](size_t n) { size_t b = (n + 255) / 256; return static_cast<unsigned>(b > 148 * 16 ? 148 * 16 : (b ? b : 1)); };
@@ -388,7 +401,7 @@ int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_a, cons
   float* partial = g.partial_elems ? w.take<float>(g.partial_elems) : nullptr;
   if (g.partial_elems && !partial) { set_error("gemm: workspace too small"); return DG_ERR_WORKSPACE_TOO_SMALL; }
   CUtensorMap mA, mB;
-  DG_PROPAGATE(make_map(&mA, oa.p, oa.rows, oa.k, oa.ld, oa.stride, a_copies, trans_a != 0));
+  DG_PROPAGATE(make_map(&mA, oa.p, oa.rows, oa.k, oa.ld, oa.stride, a_copies, trans_a != 0, kBM * g.mt));
   DG_PROPAGATE(make_map(&mB, ob.p, ob.rows, ob.k, ob.ld, ob.stride, b_copies, trans_b != 0));
   GemmParams p;
   p.C = C; p.partial = partial; p.row_scale = row_scale; p.ldc = ldc; p.stride_c = stride_c;
@@ -398,18 +411,16 @@ int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_a, cons
   p.vec_ok = (g.splits > 1) ? (N % 4 == 0)
                             : ((ldc % 4 == 0) && (stride_c % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 16 == 0));
   p.n_tiles = static_cast<int>((N + kBN - 1) / kBN);
-  const dim3 grid(static_cast<unsigned>(p.n_tiles * batch), static_cast<unsigned>((M + kBM - 1) / kBM),
+  const dim3 grid(static_cast<unsigned>(p.n_tiles * batch), static_cast<unsigned>((M + kBM * g.mt - 1) / (kBM * g.mt)),
                   static_cast<unsigned>(g.splits));
-  const size_t smem = (split3 ? 3 * 4 : 6 * 2) * kTileBytes + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
-  if (split3) {
-    static bool attr = false;
-    if (!attr) { DG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
-    gemm_nt_tf32_kernel<true><<<grid, kGemmThreads, smem, st>>>(mA, mB, p);
-  } else {
-    static bool attr = false;
-    if (!attr) { DG_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); attr = true; }
-    gemm_nt_tf32_kernel<false><<<grid, kGemmThreads, smem, st>>>(mA, mB, p);
-  }
+  const size_t smem = 192 * 1024 + 1024 /*alignment slack*/ + 256 /*barriers + tmem slot*/;
+  auto launch = [&](auto kernel) -> int {
+    DG_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kernel<<<grid, kGemmThreads, smem, st>>>(mA, mB, p);
+    return DG_OK;
+  };
+  if (split3) DG_PROPAGATE(g.mt == 2 ? launch(gemm_nt_tf32_kernel<true, 2>) : launch(gemm_nt_tf32_kernel<true, 1>));
+  else DG_PROPAGATE(g.mt == 2 ? launch(gemm_nt_tf32_kernel<false, 2>) : launch(gemm_nt_tf32_kernel<false, 1>));
   DG_CHECK_LAUNCH("gemm_tf32");
   if (g.splits > 1) {
     size_t per = static_cast<size_t>(M) * N;
