@@ -342,7 +342,12 @@ def run_b200(args):
             traffic = json.load(fh).get('%s_d%d' % (top_key[0], top_key[1]))
     roofline = {'bound': 'hbm', 'kernel': 'spmm_csr_kernel (%s, d=%d, %d-byte features)' % top_key,
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
-                'traffic': traffic, 'peak_source': peak_src, 'launches_timed': top['n'],
+                'traffic': traffic,
+                # the three readings of "fraction of HBM peak": gather-model (`frac`, L2-served re-reads counted), actual
+                # DRAM traffic per launch from the committed ncu capture, and the no-reuse lower bound (`compulsory_frac`)
+                'dram_GBps': round(traffic / (top['ms'] / top['n'] / 1e3) / 1e9, 1) if traffic else None,
+                'dram_frac': round(traffic / (top['ms'] / top['n'] / 1e3) / 1e9 / peak, 4) if traffic else None,
+                'peak_source': peak_src, 'launches_timed': top['n'],
                 'avg_launch_ms': round(top['ms'] / top['n'], 4),
                 'algorithmic_bytes_per_launch': int(top['bytes'] / top['n']),
                 'model': 'gather: nnz*(4[+4]+d*s) + n_rows*d*4 + index/scale vectors (SURVEY 8d)',

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, const int* __restrict__ perm, int64_t n_pairs,
                       const float* __restrict__ pd, const float* __restrict__ ps, const float* __restrict__ w2,
                       const float* __restrict__ w3, DropCfg drop, const float* __restrict__ z2,
-                      const float* __restrict__ dout, float* __restrict__ dz1, float* __restrict__ partials) {
+                      const float* __restrict__ dout, float* __restrict__ dz1, float* __restrict__ partials, int flush_tiles) {
   if (drop.seed_dev) drop.seed = *drop.seed_dev;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms, kept as an offset from the __shared__ array so that the compiler
@@ -479,7 +479,7 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
     }
     mbar_wait(bar2, it & 1);                             // z1 / dz2 tiles free again
     tc_fence_after();
-    if (++since_flush == kFlushTiles) {
+    if (++since_flush == flush_tiles) {
       flush_dw2();
       flushed_once = true;
       since_flush = 0;
@@ -561,7 +561,9 @@ int launch_decoder_bwd_tc(const int* src, const int* dst, const int* perm, int64
   }
   const int64_t n_tiles = (n_pairs + kBT - 1) / kBT;
   const int grid = tc_grid(n_tiles);
-  decoder_bwd_tc_kernel<<<grid, kTcThreads, kBwdTcSmem, st>>>(src, dst, perm, n_pairs, pd, ps, w2, w3, drop, z2, dout, dz1, partials);
+  const char* ft = getenv("DG_DEC_FLUSH");           // tuning switch
+  decoder_bwd_tc_kernel<<<grid, kTcThreads, kBwdTcSmem, st>>>(src, dst, perm, n_pairs, pd, ps, w2, w3, drop, z2, dout, dz1, partials,
+                                                              ft ? atoi(ft) : kFlushTiles);
   DG_CHECK_LAUNCH("decoder_bwd_tc");
   *n_ctas = grid;
   return DG_OK;
