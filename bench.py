@@ -176,7 +176,8 @@ def run_b200(args):
             step()
             th.cuda.synchronize()
             eager_launches = _lib.launch_count()
-            step = GraphedIteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
+            step = GraphedIteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs,
+                                    pipeline_aug=False if args.serial_aug else (True if args.pipeline_aug else None))
     del w
 
     def barrier():
@@ -373,7 +374,9 @@ def run_b200(args):
                                      spec['f_drug'], spec['f_dis'], spec['k']),
                       'step': 'augmentation + forward + loss + backward + clip + Adam (train.py:250-300)',
                       'aggregated_edges_per_step': int(agg_edges), 'scale': args.scale,
-                      'launch': 'one CUDA-graph replay per step' if args.cuda_graph else 'eager launches',
+                      'launch': ('one CUDA-graph replay per step' + (' (augmentation of step i+1 on a parallel branch of step i)'
+                                                                   if getattr(step, 'staged', None) is not None else ''))
+                                if args.cuda_graph else 'eager launches',
                       'l2': 'inputs larger than L2 (gathered operand %.0f MB, indices %.0f MB per SpMM)'
                             % (top['bmin'] / top['n'] / 1e6, top['nnz'] / top['n'] * 4 / 1e6)
                             if top['bmin'] / top['n'] > 126e6 else 'working set fits L2; no flush between steps',
@@ -536,6 +539,10 @@ def main():
     ap.add_argument('--cpu-scale', type=float, default=0.0, help='scale of the CPU sample (default: scale/40 for syn*)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--eager', action='store_true', help='per-kernel launches instead of one CUDA-graph replay per step')
+    ap.add_argument('--serial-aug', action='store_true',
+                    help='CUDA-graph mode: keep the augmentation inside its own iteration (default: by size -- at the small '
+                         'real-dataset shapes the draw for iteration i+1 runs on a second stream beside iteration i)')
+    ap.add_argument('--pipeline-aug', action='store_true', help='force the pipelined augmentation at any size')
     ap.add_argument('--cuda-graph', action='store_true',
                     help='replay the whole training iteration from one captured CUDA graph (launch-bound small shapes)')
     ap.add_argument('--messages', default='f32', choices=['f32', 'bf16'],

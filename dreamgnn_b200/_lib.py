@@ -5,13 +5,13 @@ device, the call raises. Build with `python -m dreamgnn_b200.build`.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_ulonglong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_ulonglong, c_void_p
 
 import torch as th
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'lib', 'libdreamgnn.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _P = c_void_p
 _SIGNATURES = {
@@ -41,6 +41,10 @@ _SIGNATURES = {
                                c_int64, _P, c_int, _P, c_size_t, _P]),
     'dg_gemm_f32': (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                             c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
+    'dg_colsum_workspace_bytes': (c_size_t, [c_int64, c_int64]),
+    'dg_colsum_f32': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    'dg_center_normalize_f64': (c_int, [_P, c_int64, _P, c_int64, c_int64, c_double, _P, c_int64, _P, _P]),
+    'dg_center_normalize_bwd_f64': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P]),
     'dg_topk_rows_f64': (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P]),
     'dg_knn_graph_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'dg_knn_graph_from_neighbors': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -215,10 +215,15 @@ class GCMCLayer(nn.Module):
                 if MESSAGE_DTYPE != th.float32:
                     h = h.to(MESSAGE_DTYPE)
                 agg = ops.spmm(blk.csr, h.reshape(blk.num_rel * blk.n_src, dp), src_scale=scale, dst_scale=ci, tag='gcmc')
-            out[dst_type] = agg[:, :D] if dp != D else agg
+            out[dst_type] = agg
+        # The padded message columns (341 -> 344) are exactly zero through aggregation, activation and dropout, so the
+        # tail runs on the padded width with zero weight columns appended to ifc / ufc: no slice copy forward, no
+        # re-padding of the gradient backward, and the GEMM operands stay 16-byte aligned for TMA.
         drug = self.dropout(self.agg_act(out['drug']))
         dis = self.dropout(self.agg_act(out['disease']))
-        return (ops.linear(drug, self.ifc.weight, self.ifc.bias), ops.linear(dis, self.ufc.weight, self.ufc.bias))
+        wi = _pad_cols(self.ifc.weight, mult) if drug.shape[1] != D else self.ifc.weight
+        wu = wi if self.ufc is self.ifc else (_pad_cols(self.ufc.weight, mult) if dis.shape[1] != D else self.ufc.weight)
+        return (ops.linear(drug, wi, self.ifc.bias), ops.linear(dis, wu, self.ufc.bias))
 
 
 class GraphConvolution(nn.Module):

@@ -167,6 +167,97 @@ def csr_dropout(csr, flags, n_keep):
 
 
 # ------------------------------------------------------------------------------------------------
+# row-streaming helpers (rowops.cu)
+# ------------------------------------------------------------------------------------------------
+def _rows_ok(t):
+    return (t.dim() == 2 and t.dtype == th.float32 and t.stride(1) == 1 and t.shape[1] % 4 == 0
+            and t.stride(0) % 4 == 0 and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0)
+
+
+def colsum(x, gate=None, want_masked=False):
+    """Deterministic x.sum(0) of a [n, d] fp32 matrix in one pass; with `gate` the sum (and, if `want_masked`,
+    the returned matrix) is of x * (gate > 0) -- F.relu's backward fused with the bias gradient.
+    Returns sum [d] or (masked [n, d], sum [d]). Shapes the kernel cannot address (d % 4 != 0, unaligned rows)
+    take the equivalent torch expression on the device."""
+    if not x.is_cuda:
+        raise RuntimeError('dreamgnn_b200.colsum needs CUDA tensors (no CPU fallback)')
+    if not (x.dim() == 2 and x.shape[0] > 0 and _rows_ok(x) and (gate is None or (_rows_ok(gate) and gate.shape == x.shape))):
+        y = x if gate is None else x * (gate > 0).to(x.dtype)
+        return (y, y.sum(0)) if want_masked else y.sum(0)
+    lib = L.load()
+    n, d = x.shape
+    out = th.empty(d, dtype=th.float32, device=x.device)
+    y = th.empty((n, d), dtype=th.float32, device=x.device) if (want_masked and gate is not None) else None
+    ws = L.workspace(lib.dg_colsum_workspace_bytes(n, d), x.device)
+    L.check(lib.dg_colsum_f32(x.data_ptr(), x.stride(0), None if gate is None else gate.data_ptr(),
+                              0 if gate is None else gate.stride(0), L.ptr(y), d, n, d, L.ptr(out), L.ptr(ws), ws.numel(),
+                              L.stream()), 'colsum')
+    if want_masked:
+        return (x if y is None else y), out
+    return out
+
+
+class GramCommonLoss(th.autograd.Function):
+    """common_loss (utils.py:87-95) in its Gram-matrix form, forward and backward with explicit kernels:
+
+        Z = [z1 | z2]  (rows centred by the column mean, L2-normalised, float64)      dg_colsum + dg_center_normalize
+        G = Z^T Z = [[G11, G12], [G21, G22]]                                          one float64 GEMM (library)
+        loss = (|G11|^2 + |G22|^2 - 2 |G12|^2) / n^2 = sum(G * G * S) / n^2,  S = [[+1, -1], [-1, +1]]
+        dL/dZ = (4 / n^2) Z (G * S);   dc = (gz - z <z, gz>) / |c|;   dx = dc - colmean(dc)
+
+    ~25 launches per call against ~95 for the autograd-traced torch expression; same value (float64 accumulation)."""
+
+    @staticmethod
+    def forward(ctx, emb1, emb2):
+        lib = L.load()
+        n, d = emb1.shape
+        dev = emb1.device
+        z = th.empty((n, 2 * d), dtype=th.float64, device=dev)
+        inv = th.empty((2, n), dtype=th.float64, device=dev)
+        for i, e in enumerate((emb1, emb2)):
+            cs = colsum(e)
+            L.check(lib.dg_center_normalize_f64(e.data_ptr(), e.stride(0), L.ptr(cs), n, d, 1e-12,
+                                                z.data_ptr() + i * d * 8, 2 * d, inv.data_ptr() + i * n * 8, L.stream()),
+                    'center_normalize')
+        g = z.t() @ z                                                     # [2d, 2d] float64
+        gs = g.clone()                                                    # G * S: the off-diagonal blocks negated
+        blocks = gs.view(2, d, 2, d)
+        blocks[0, :, 1, :].neg_()
+        blocks[1, :, 0, :].neg_()
+        loss = ((g * gs).sum() / float(n) / float(n)).float()
+        ctx.save_for_backward(z, inv, gs)
+        ctx.shape = (n, d)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.load()
+        z, inv, gs = ctx.saved_tensors
+        n, d = ctx.shape
+        gz = z @ (gs * (gout.double() * (4.0 / float(n) / float(n))))      # [n, 2d] float64
+        grads = []
+        for i in range(2):
+            if not ctx.needs_input_grad[i]:
+                grads.append(None)
+                continue
+            dc = th.empty((n, d), dtype=th.float32, device=z.device)
+            L.check(lib.dg_center_normalize_bwd_f64(gz.data_ptr() + i * d * 8, 2 * d, z.data_ptr() + i * d * 8, 2 * d,
+                                                    inv.data_ptr() + i * n * 8, n, d, L.ptr(dc), d, L.stream()),
+                    'center_normalize_bwd')
+            grads.append(dc.sub_(colsum(dc) / float(n)))
+        return tuple(grads)
+
+
+def gram_common_loss(emb1, emb2):
+    """Fused common_loss in Gram form for [n, d] fp32 CUDA embeddings (d % 4 == 0)."""
+    if not (emb1.is_cuda and emb2.is_cuda):
+        raise RuntimeError('dreamgnn_b200.gram_common_loss needs CUDA tensors (no CPU fallback)')
+    if emb1.shape != emb2.shape or not (_rows_ok(emb1) and _rows_ok(emb2)):
+        raise ValueError('gram_common_loss: two [n, d] fp32 matrices with 16-byte aligned rows expected')
+    return GramCommonLoss.apply(emb1, emb2)
+
+
+# ------------------------------------------------------------------------------------------------
 # SpMM
 # ------------------------------------------------------------------------------------------------
 # Optional launch log for bench.py's roofline: when PROFILE is a list every SpMM launch appends
@@ -220,9 +311,13 @@ class SpMMFunction(th.autograd.Function):
     def backward(ctx, dout):
         src_scale, dst_scale, out = ctx.saved_tensors
         dout = dout.contiguous()
-        if ctx.relu:
-            dout = dout * (out > 0).to(dout.dtype)
-        dbias = dout.sum(0) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        want_bias = ctx.has_bias and ctx.needs_input_grad[1]
+        dbias = None
+        if ctx.relu:                                      # relu mask (+ bias gradient) in one pass over dout
+            dout, s = colsum(dout, gate=out, want_masked=True)
+            dbias = s if want_bias else None
+        elif want_bias:
+            dbias = colsum(dout)
         dx = None
         if ctx.needs_input_grad[0]:
             # d x[j] = src_scale[j] * sum_{i : j in row i} vals * dst_scale[i] * dout[i]  -> transposed CSR
@@ -479,7 +574,7 @@ class LinearFunction(th.autograd.Function):
         dy = dy.contiguous()
         dx = gemm(dy, w, trans_b=True) if ctx.needs_input_grad[0] else None
         dw = gemm(dy, x, trans_a=True, trans_b=True) if ctx.needs_input_grad[1] else None
-        db = dy.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        db = colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 
 

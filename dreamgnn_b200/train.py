@@ -98,15 +98,22 @@ class TrainState:
         self.drug_sim_feat, self.dis_sim_feat = drug_sim_feat, dis_sim_feat
 
 
-def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_params, beta=0.001, grad_clip=1.0,
-                    common_loss_fn=common_loss):
-    """One training iteration exactly as train.py:250-300; returns the (device) loss tensor."""
-    model.train()
-    aug = augment_graph_data({
+def augment_state(state, aug_methods, aug_params):
+    """The per-iteration augmentation of train.py:254-277 on the resident training inputs."""
+    return augment_graph_data({
         'enc_graph': state.enc_graph, 'drug_graph': state.drug_graph, 'disease_graph': state.dis_graph,
         'drug_feature_graph': state.drug_feature_graph, 'disease_feature_graph': state.disease_feature_graph,
         'drug_feat': state.drug_feat, 'disease_feat': state.dis_feat,
         'drug_sim_feat': state.drug_sim_feat, 'disease_sim_feat': state.dis_sim_feat}, aug_methods, aug_params)
+
+
+def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_params, beta=0.001, grad_clip=1.0,
+                    common_loss_fn=common_loss, aug=None):
+    """One training iteration exactly as train.py:250-300; returns the (device) loss tensor. `aug` may carry
+    an augmentation drawn ahead of time (graphed.GraphedIteration pipelines it beside the previous iteration)."""
+    model.train()
+    if aug is None:
+        aug = augment_state(state, aug_methods, aug_params)
     pred, drug_out, drug_sim_out, dis_out, dis_sim_out = model(
         aug['enc_graph'], state.dec_graph, aug['drug_graph'], aug['drug_sim_feat'], aug['drug_feat'],
         aug['disease_graph'], aug['disease_sim_feat'], aug['disease_feat'], aug['drug_feature_graph'],

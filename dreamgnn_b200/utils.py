@@ -35,7 +35,19 @@ def common_loss(emb1, emb2):
 def common_loss_gram(emb1, emb2):
     """Same value as `common_loss` without the N x N matrices:
     ||Z1 Z1^T - Z2 Z2^T||_F^2 = ||Z1^T Z1||_F^2 + ||Z2^T Z2||_F^2 - 2 ||Z1^T Z2||_F^2.
-    Used only where N x N does not fit (the synthetic 100k-node shapes); accumulates in float64."""
+    Used only where N x N does not fit (the synthetic 100k-node shapes); accumulates in float64. Runs as the
+    explicit-kernel autograd function `ops.GramCommonLoss` where the layout allows (DG_COMMON_LOSS=torch keeps the
+    traced torch expression below, which is also what the tests compare it with)."""
+    import os
+    from . import ops
+    if (os.environ.get('DG_COMMON_LOSS', 'fused') != 'torch' and emb1.is_cuda and emb1.dtype == th.float32
+            and emb2.dtype == th.float32 and emb1.shape == emb2.shape and ops._rows_ok(emb1) and ops._rows_ok(emb2)):
+        return ops.gram_common_loss(emb1, emb2)
+    return common_loss_gram_torch(emb1, emb2)
+
+
+def common_loss_gram_torch(emb1, emb2):
+    """The Gram form written with torch ops (autograd-traced)."""
     n = emb1.shape[0]
     z1 = th.nn.functional.normalize(emb1 - th.mean(emb1, dim=0, keepdim=True), p=2, dim=1).double()
     z2 = th.nn.functional.normalize(emb2 - th.mean(emb2, dim=0, keepdim=True), p=2, dim=1).double()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 2
+#define DG_ABI_VERSION 3
 
 #define DG_OK 0
 #define DG_ERR_INVALID_ARGUMENT (-1)
@@ -176,6 +176,29 @@ DG_API int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_
                        int64_t stride_b, int trans_b, float* C, int64_t ldc, int64_t stride_c, int64_t M, int64_t N,
                        int64_t K, int64_t batch, const float* row_scale, int precision, void* workspace,
                        size_t workspace_bytes, dg_stream_t stream);
+
+/* ---- row-streaming helpers around the aggregation kernels ------------------------------------ */
+/* Deterministic column sums of a row-major fp32 matrix (fixed slab partition, fixed summation order, no atomics):
+ *   out[j] = sum_i y[i][j],  y = x            (gate == NULL)
+ *                            y = x * (gate>0) (gate != NULL: the ReLU mask of the aggregation epilogue)
+ * and, when y != NULL, y is written ([n_rows, d], leading dimension ldy; must not alias x). One pass over the matrix.
+ * Replaces autograd's `grad.sum(0)` for the GraphConvolution / nn.Linear bias gradients (backward of layers.py:311-314,
+ * layers.py:139-142) and the `grad * (out > 0)` of F.relu's backward (layers.py:247), and gives the column means of
+ * utils.py:89-90. d % 4 == 0, rows 16-byte aligned. */
+DG_API size_t dg_colsum_workspace_bytes(int64_t n_rows, int64_t d);
+DG_API int dg_colsum_f32(const float* x, int64_t ldx, const float* gate, int64_t ldg, float* y, int64_t ldy,
+                         int64_t n_rows, int64_t d, float* out, void* workspace, size_t workspace_bytes,
+                         dg_stream_t stream);
+/* Rows of common_loss (utils.py:87-95): z[i,:] = c_i / max(||c_i||_2, eps) with c_i = x[i,:] - colsum/n_rows, widened to
+ * float64 (the Gram-matrix form of the loss accumulates in float64); inv_norm[i] = 1 / max(||c_i||, eps).
+ * z is [n_rows, d] with leading dimension ldz (two embeddings are written side by side into one [n, 2d] operand). */
+DG_API int dg_center_normalize_f64(const float* x, int64_t ldx, const float* colsum, int64_t n_rows, int64_t d,
+                                   double eps, double* z, int64_t ldz, double* inv_norm, dg_stream_t stream);
+/* Backward of the row normalisation: dc[i,:] = (gz[i,:] - z[i,:] * <z[i,:], gz[i,:]>) * inv_norm[i] (fp32 out); the
+ * caller subtracts the column mean of dc afterwards (backward of the centring). */
+DG_API int dg_center_normalize_bwd_f64(const double* gz, int64_t ldgz, const double* z, int64_t ldz,
+                                       const double* inv_norm, int64_t n_rows, int64_t d, float* dc, int64_t lddc,
+                                       dg_stream_t stream);
 
 /* ---- kNN similarity graphs (data_loader.py:278-344, utils.py:11-27) ------------------------- */
 /* Per row of a float64 similarity block [n_rows, n_cols] (leading dimension ld), the k largest

@@ -398,3 +398,86 @@ def test_project_autograd_on_tensor_cores(dev):
     yr.backward(gout.double())
     assert H.rel_err(y.detach().cpu(), yr.detach()) <= FP32_TOL
     assert H.rel_err(xg.grad.cpu(), xr.grad) <= FP32_TOL and H.rel_err(wg.grad.cpu(), wr.grad) <= FP32_TOL
+
+
+# ---- row-streaming helpers (rowops.cu) ------------------------------------------------------------------
+@pytest.mark.parametrize('n,d', [(0, 8), (1, 4), (7, 128), (1000, 344), (5003, 768), (100001, 128), (300, 1024)])
+@pytest.mark.parametrize('gated', [False, True])
+def test_colsum_is_deterministic_and_exact(dev, n, d, gated):
+    gen = th.Generator().manual_seed(n + d)
+    x = th.randn(n, d, generator=gen)
+    gate = th.randn(n, d, generator=gen) if gated else None
+    xs = x.to(dev)
+    gs = gate.to(dev) if gated else None
+    masked, s = ops().colsum(xs, gate=gs, want_masked=True)
+    want_m = x.double() * (gate > 0).double() if gated else x.double()
+    assert th.equal(masked.cpu().double(), want_m)                           # the mask is exact
+    want = want_m.sum(0)
+    err = (s.cpu().double() - want).abs().max().item() if n else 0.0
+    assert err <= 1e-6 * max(1.0, want_m.abs().sum(0).max().item() if n else 1.0)
+    s2 = ops().colsum(xs, gate=gs)
+    assert th.equal(s, s2)                                                    # fixed summation order: bit-identical
+    # a strided view (rows 16-byte aligned) goes through the kernel too; an unaligned one takes the torch expression
+    if d >= 8 and n:
+        v = xs[:, 4:d]
+        np.testing.assert_allclose(ops().colsum(v).cpu().numpy(), x[:, 4:d].double().sum(0).numpy(), rtol=0, atol=1e-3)
+        u = xs[:, 1:d]
+        np.testing.assert_allclose(ops().colsum(u).cpu().numpy(), x[:, 1:d].double().sum(0).numpy(), rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize('n,d', [(3, 4), (50, 16), (777, 128), (20000, 128), (3000, 64)])
+def test_gram_common_loss_matches_reference_form(dev, n, d):
+    """utils.py:87-95 (N x N form) on CPU in float64 vs the explicit-kernel Gram form: value and both gradients."""
+    from dreamgnn_b200.utils import common_loss, common_loss_gram, common_loss_gram_torch
+    gen = th.Generator().manual_seed(n * 31 + d)
+    a = th.randn(n, d, generator=gen) + 0.3
+    b = a * 0.5 + th.randn(n, d, generator=gen)
+    ref_in = [t.double().requires_grad_(True) for t in (a, b)]
+    ref = common_loss(*ref_in)
+    ref.backward()
+    got_in = [t.to(dev).requires_grad_(True) for t in (a, b)]
+    got = common_loss_gram(*got_in)
+    assert got.dtype == th.float32
+    (got * 3.0).backward()
+    assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-12
+    for g, r in zip(got_in, ref_in):
+        assert H.rel_err(g.grad.cpu().double() / 3.0, r.grad) <= FP32_TOL
+    # and the traced torch expression it replaces
+    tor_in = [t.to(dev).requires_grad_(True) for t in (a, b)]
+    tor = common_loss_gram_torch(*tor_in)
+    tor.backward()
+    assert abs(got.item() - tor.item()) <= 1e-5 * abs(tor.item()) + 1e-12
+    for g, t in zip(got_in, tor_in):
+        assert H.rel_err(g.grad / 3.0, t.grad) <= FP32_TOL
+
+
+def test_gram_common_loss_one_sided_gradient(dev):
+    from dreamgnn_b200.utils import common_loss_gram, common_loss_gram_torch
+    gen = th.Generator().manual_seed(3)
+    a, b = th.randn(500, 32, generator=gen).to(dev), th.randn(500, 32, generator=gen).to(dev)
+    a1, a2 = a.clone().requires_grad_(True), a.clone().requires_grad_(True)
+    common_loss_gram(a1, b).backward()
+    common_loss_gram_torch(a2, b).backward()
+    assert H.rel_err(a1.grad, a2.grad) <= FP32_TOL
+
+
+def test_spmm_relu_bias_backward_fused(dev):
+    """GraphConvolution epilogue (layers.py:311-314 + F.relu): bias gradient and ReLU mask from one pass."""
+    rng = np.random.default_rng(11)
+    n, d, nnz = 400, 64, 3000
+    row, col = rng.integers(0, n, nnz), rng.integers(0, n, nnz)
+    vals = rng.random(nnz).astype(np.float32)
+    csr = ops().CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), n, n, th.tensor(vals, device=dev))
+    x = th.randn(n, d, device=dev, requires_grad=True)
+    bias = th.randn(d, device=dev, requires_grad=True)
+    out = ops().spmm(csr, x, bias=bias, relu=True)
+    w = th.randn(n, d, device=dev)
+    (out * w).sum().backward()
+    A = th.zeros(n, n, dtype=th.float64)
+    A.index_put_((th.tensor(row), th.tensor(col)), th.tensor(vals).double(), accumulate=True)
+    xr, br = x.detach().cpu().double().requires_grad_(True), bias.detach().cpu().double().requires_grad_(True)
+    ref = th.relu(A @ xr + br)
+    (ref * w.cpu().double()).sum().backward()
+    assert H.rel_err(out.detach().cpu().double(), ref.detach()) <= FP32_TOL
+    assert H.rel_err(x.grad.cpu().double(), xr.grad) <= FP32_TOL
+    assert H.rel_err(bias.grad.cpu().double(), br.grad) <= FP32_TOL
