@@ -177,7 +177,8 @@ def run_b200(args):
             th.cuda.synchronize()
             eager_launches = _lib.launch_count()
             step = GraphedIteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs,
-                                    pipeline_aug=False if args.serial_aug else (True if args.pipeline_aug else None))
+                                    pipeline_aug=False if args.serial_aug else (True if args.pipeline_aug else None),
+                                    parallel_routes=False if args.serial_aug else None)
     del w
 
     def barrier():

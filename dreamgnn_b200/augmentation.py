@@ -127,7 +127,7 @@ class GraphAugmentation:
             return None
         if not isinstance(features, th.Tensor):
             features = th.tensor(features, dtype=th.float32, device='cuda')
-        return features + th.randn_like(features) * noise_scale
+        return th.add(features, th.randn_like(features), alpha=noise_scale)      # features + noise * scale, one pass
 
     @staticmethod
     def sparse_graph_noise(graph, noise_scale=0.05):

@@ -81,13 +81,34 @@ colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, const float* __r
   }
 }
 
-// out[col] = sum over slabs in slab order (double accumulator: the only long serial chain of the reduction)
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int slabs, int d, float* __restrict__ out) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= d) return;
-  double s = 0.0;
-  for (int i = 0; i < slabs; ++i) s += static_cast<double>(partial[static_cast<int64_t>(i) * d + col]);
-  out[col] = static_cast<float>(s);
+// out[col] = sum of the slab partials in a fixed order: 8 warps each sum a contiguous range of slabs for 32 columns
+// (independent loads, double accumulators), then the 8 range sums are added in range order.
+constexpr int kFinishGroups = 8;
+__global__ void __launch_bounds__(32 * kFinishGroups)
+colsum_finish_kernel(const float* __restrict__ partial, int slabs, int d, float* __restrict__ out) {
+  __shared__ double red[kFinishGroups][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int per = (slabs + kFinishGroups - 1) / kFinishGroups;
+  const int s0 = grp * per, s1 = min(slabs, s0 + per);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  if (col < d) {
+    int i = s0;
+    for (; i + 3 < s1; i += 4) {
+      const float v0 = partial[static_cast<int64_t>(i) * d + col], v1 = partial[static_cast<int64_t>(i + 1) * d + col];
+      const float v2 = partial[static_cast<int64_t>(i + 2) * d + col], v3 = partial[static_cast<int64_t>(i + 3) * d + col];
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    }
+    for (; i < s1; ++i) a0 += partial[static_cast<int64_t>(i) * d + col];
+  }
+  red[grp][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (grp == 0 && col < d) {
+    double s = red[0][lane];
+#pragma unroll
+    for (int g = 1; g < kFinishGroups; ++g) s += red[g][lane];
+    out[col] = static_cast<float>(s);
+  }
 }
 
 // z[row,:] = (x[row,:] - colsum/n) * inv, inv = 1 / max(||x[row,:] - colsum/n||_2, eps); warp per row
@@ -195,7 +216,7 @@ int dg_colsum_f32(const float* x, int64_t ldx, const float* gate, int64_t ldg, f
   else
     colsum_partial_kernel<false, false><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, nullptr, 0, nullptr, 0, n_rows, di, partial);
   DG_CHECK_LAUNCH("colsum_partial");
-  colsum_finish_kernel<<<static_cast<unsigned>((d + 127) / 128), 128, 0, st>>>(partial, slabs, di, out);
+  colsum_finish_kernel<<<static_cast<unsigned>((d + 31) / 32), 32 * kFinishGroups, 0, st>>>(partial, slabs, di, out);
   DG_CHECK_LAUNCH("colsum_finish");
   return DG_OK;
 }

@@ -138,7 +138,8 @@ class StagedAugmentation:
 
 class GraphedIteration:
     def __init__(self, model, optimizer, state, rel_loss_fn=None, aug_methods=('edge_dropout', 'feature_noise'),
-                 aug_params=None, beta=0.001, grad_clip=1.0, common_loss_fn=common_loss, warmup=3, pipeline_aug=None):
+                 aug_params=None, beta=0.001, grad_clip=1.0, common_loss_fn=common_loss, warmup=3, pipeline_aug=None,
+                 parallel_routes=None):
         if not all(g.get('capturable', False) for g in optimizer.param_groups):
             raise ValueError('the optimizer must be built with capturable=True (e.g. torch.optim.Adam(..., capturable=True))')
         self.model, self.optimizer, self.state = model, optimizer, state
@@ -163,8 +164,13 @@ class GraphedIteration:
                     'disease_sim_feat': state.dis_sim_feat}
 
         self.staged = None
+        small = int(state.labels.numel()) < PIPELINE_MAX_PAIRS
+        if parallel_routes is None:
+            parallel_routes = small
+        if hasattr(model, 'parallel_routes'):
+            model.parallel_routes = bool(parallel_routes)       # GCMC route || FGCN route as two branches of the graph
         if pipeline_aug is None:
-            pipeline_aug = int(state.labels.numel()) < PIPELINE_MAX_PAIRS
+            pipeline_aug = small
         if pipeline_aug and aug_methods:
             try:
                 # the first replay trains on this eagerly drawn augmentation
@@ -186,6 +192,8 @@ class GraphedIteration:
                     self.staged.refresh(augment_state(state, aug_methods, aug_params))
                 self.loss = self._step(self._live)
                 main.wait_stream(self._aug_stream)                       # join
+        if hasattr(model, 'parallel_routes'):
+            model.parallel_routes = False                                # the branches are in the graph; eager calls stay serial
 
     def __call__(self):
         """Run one iteration; returns the (static) device tensor holding its loss."""

@@ -107,6 +107,31 @@ def test_net_forward_eval(case, dev):
         assert H.rel_err(a.cpu(), b) <= FP32_TOL
 
 
+def test_parallel_routes_are_bit_identical(case, dev):
+    """Net.parallel_routes records the GCMC route and the FGCN route on two streams (forward and, through autograd's
+    stream replay, backward): same kernels, same order inside each route -> bit-identical outputs and gradients."""
+    from dreamgnn_b200.utils import common_loss
+    name, g, built, knn = case
+    labels = th.tensor(g['train.labels']).to(dev)
+    res = {}
+    for flag in (False, True):
+        net = _net(g, name, dev).train()
+        net.parallel_routes = flag
+        with th.cuda.stream(th.cuda.Stream()):
+            out = net(*_inputs(g, built, knn, dev))
+            loss = th.nn.BCEWithLogitsLoss()(out[0].squeeze(-1), labels) + 0.001 * (
+                common_loss(out[1], out[2]) + common_loss(out[3], out[4]))
+            loss.backward()
+        th.cuda.synchronize()
+        res[flag] = ([o.detach().clone() for o in out], {k: p.grad.clone() for k, p in net.named_parameters()
+                                                          if p.grad is not None})
+    for a, b in zip(res[False][0], res[True][0]):
+        assert th.equal(a, b)
+    assert res[False][1].keys() == res[True][1].keys()
+    for k in res[False][1]:
+        assert th.equal(res[False][1][k], res[True][1][k]), k
+
+
 def test_net_gradients(case, dev):
     from dreamgnn_b200.utils import common_loss
     name, g, built, knn = case
