@@ -191,12 +191,13 @@ class GCMCLayer(nn.Module):
         weights = self._relation_weights()
         D = self.msg_units
         mult = 8 if MESSAGE_DTYPE == th.bfloat16 else 4
-        out = {}
         seen = []
         for c in graph.canonical_etypes:                 # blocks in the reference's etype order
             if c[2] not in seen:
                 seen.append(c[2])
-        for dst_type in seen:
+
+        def aggregate(dst_type):
+            """All relations into one node type: one batched projection, one SpMM."""
             blk = graph.block(dst_type)
             x = feats[blk.src_type]
             part = getattr(graph, 'partition', None)             # row-partitioned graph: x holds the owned rows
@@ -215,15 +216,27 @@ class GCMCLayer(nn.Module):
                 if MESSAGE_DTYPE != th.float32:
                     h = h.to(MESSAGE_DTYPE)
                 agg = ops.spmm(blk.csr, h.reshape(blk.num_rel * blk.n_src, dp), src_scale=scale, dst_scale=ci, tag='gcmc')
-            out[dst_type] = agg
-        # The padded message columns (341 -> 344) are exactly zero through aggregation, activation and dropout, so the
-        # tail runs on the padded width with zero weight columns appended to ifc / ufc: no slice copy forward, no
-        # re-padding of the gradient backward, and the GEMM operands stay 16-byte aligned for TMA.
-        drug = self.dropout(self.agg_act(out['drug']))
-        dis = self.dropout(self.agg_act(out['disease']))
-        wi = _pad_cols(self.ifc.weight, mult) if drug.shape[1] != D else self.ifc.weight
-        wu = wi if self.ufc is self.ifc else (_pad_cols(self.ufc.weight, mult) if dis.shape[1] != D else self.ufc.weight)
-        return (ops.linear(drug, wi, self.ifc.bias), ops.linear(dis, wu, self.ufc.bias))
+            return agg
+
+        def tail(dst_type, agg):
+            """Activation, dropout, output layer of one node type."""
+            # The padded message columns (341 -> 344) are exactly zero through aggregation, activation and dropout, so
+            # the tail runs on the padded width with zero weight columns appended to ifc / ufc: no slice copy forward,
+            # no re-padding of the gradient backward, and the GEMM operands stay 16-byte aligned for TMA.
+            y = self.dropout(self.agg_act(agg))
+            fc = self.ifc if dst_type == 'drug' else self.ufc
+            w = _pad_cols(fc.weight, mult) if y.shape[1] != D else fc.weight
+            return ops.linear(y, w, fc.bias)
+
+        missing = [t for t in ('drug', 'disease') if t not in seen]
+        if missing:
+            raise KeyError('no relation into node type %r' % missing[0])
+        if ops.PARALLEL_BRANCHES:                                  # the two node types as parallel stream branches
+            drug, dis = ops.branches([lambda: tail('drug', aggregate('drug')), lambda: tail('disease', aggregate('disease'))])
+            return drug, dis
+        # serial: the reference's dropout draw order (cj per etype in canonical order, then drug, then disease)
+        aggs = {t: aggregate(t) for t in seen}
+        return tail('drug', aggs['drug']), tail('disease', aggs['disease'])
 
 
 class GraphConvolution(nn.Module):
@@ -311,6 +324,16 @@ class FGCN(nn.Module):
             emb1_sim = self.FGCN_drug(drug_sim_feat, drug_graph)
             emb2_sim = self.FGCN_disease(disease_sim_feat, dis_graph)
             return emb1_sim, emb2_sim, emb1_sim, None, emb2_sim, None
+        if ops.PARALLEL_BRANCHES:
+            # the two node types as parallel stream branches (dropout draws then go drug, drug, disease, disease)
+            def side(gcn, x, g_sim, g_feat, fusion):
+                e_sim, e_feat = gcn.forward_shared(x, [g_sim, g_feat])
+                fused = th.relu(ops.linear(th.cat([e_sim, e_feat], dim=1), fusion.weight, fusion.bias))
+                return F.dropout(fused, p=self.dropout, training=self.training), e_sim, e_feat
+            (emb1, emb1_sim, emb1_feat), (emb2, emb2_sim, emb2_feat) = ops.branches([
+                lambda: side(self.FGCN_drug, drug_sim_feat, drug_graph, drug_feature_graph, self.drug_fusion),
+                lambda: side(self.FGCN_disease, disease_sim_feat, dis_graph, disease_feature_graph, self.disease_fusion)])
+            return emb1, emb2, emb1_sim, emb1_feat, emb2_sim, emb2_feat
         if self.training and self.dropout > 0:
             # keep the reference's dropout draw order: drug(sim), disease(sim), drug(feat), disease(feat)
             s_d, s_s = self.FGCN_drug.gc1.support(drug_sim_feat), self.FGCN_disease.gc1.support(disease_sim_feat)

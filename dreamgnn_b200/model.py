@@ -9,6 +9,7 @@ import torch as th
 import torch.nn as nn
 
 from . import layers as L
+from . import ops
 from .utils import get_activation
 
 
@@ -36,7 +37,6 @@ class Net(nn.Module):
         self.attention = L.Attention(args.gcn_out_units, dropout_rate=args.attention_dropout)
         self.decoder = L.MLPDecoder(in_units=args.gcn_out_units, dropout_rate=args.dropout)
         self.parallel_routes = False        # not part of the reference API: see `embed`
-        self._route_stream = None
 
     def _topology_route(self, enc_graph, drug, dis, two_stage):
         """Stacked GCMC layers with the 1/(l+1)-weighted sum of their outputs (model.py:67-76)."""
@@ -55,26 +55,15 @@ class Net(nn.Module):
         """Everything of `forward` up to the decoder: the four route outputs and the two fused node embeddings the
         decoder scores pairs from (model.py:65-97). Not part of the reference API: `forward` is this + the decoder,
         and the all-pairs scoring of `predict.get_top_novel_predictions` calls it once instead of once per batch."""
-        if self.parallel_routes and drug_feat.is_cuda:
-            # The topology route (GCMC layers on the association graph) and the feature route (FGCN on the kNN graphs)
-            # share no intermediate: record them as two branches (autograd replays each backward node on its forward
-            # stream, so the backward forks the same way). Pays on the launch-bound real-dataset shapes, where neither
-            # branch fills the GPU; `graphed.GraphedIteration` switches it on for those.
-            main = th.cuda.current_stream()
-            if self._route_stream is None:
-                self._route_stream = th.cuda.Stream(device=drug_feat.device)
-            self._route_stream.wait_stream(main)
-            with th.cuda.stream(self._route_stream):
-                drug_sim_out, dis_sim_out = self.FGCN(drug_graph, drug_sim_feat, dis_graph, disease_sim_feat,
-                                                      drug_feature_graph, disease_feature_graph)[:2]
-            drug_out, dis_out = self._topology_route(enc_graph, drug_feat, dis_feat, Two_Stage)
-            main.wait_stream(self._route_stream)
-            drug_sim_out.record_stream(main)
-            dis_sim_out.record_stream(main)
-        else:
-            drug_out, dis_out = self._topology_route(enc_graph, drug_feat, dis_feat, Two_Stage)
-            drug_sim_out, dis_sim_out = self.FGCN(drug_graph, drug_sim_feat, dis_graph, disease_sim_feat,
-                                                  drug_feature_graph, disease_feature_graph)[:2]
+        # The topology route (GCMC layers on the association graph) and the feature route (FGCN on the kNN graphs)
+        # share no intermediate: with `parallel_routes` (or ops.PARALLEL_BRANCHES) they -- and the per-node-type halves
+        # inside them -- are recorded as parallel stream branches. Pays on the launch-bound real-dataset shapes, where
+        # no single branch fills the GPU; `graphed.GraphedIteration` switches it on for those.
+        with ops.parallel_branches(self.parallel_routes and drug_feat.is_cuda):
+            (drug_out, dis_out), (drug_sim_out, dis_sim_out) = ops.branches([
+                lambda: self._topology_route(enc_graph, drug_feat, dis_feat, Two_Stage),
+                lambda: self.FGCN(drug_graph, drug_sim_feat, dis_graph, disease_sim_feat, drug_feature_graph,
+                                  disease_feature_graph)[:2]])
         return (drug_out, drug_sim_out, dis_out, dis_sim_out,
                 self._fuse(drug_out, drug_sim_out), self._fuse(dis_out, dis_sim_out))
 

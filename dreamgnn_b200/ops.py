@@ -167,6 +167,64 @@ def csr_dropout(csr, flags, n_keep):
 
 
 # ------------------------------------------------------------------------------------------------
+# independent sub-computations as parallel stream branches
+# ------------------------------------------------------------------------------------------------
+# Off by default. `graphed.GraphedIteration` switches it on while it captures the launch-bound real-dataset shapes:
+# the branches then become parallel paths of the CUDA graph (forward, and -- autograd replays every backward node on
+# the stream of its forward -- backward too). Same kernels, same order inside each branch: results are bit-identical.
+PARALLEL_BRANCHES = False
+
+
+class parallel_branches:
+    """Context manager: `with parallel_branches(True): ...` enables `branches()` forking inside the block."""
+
+    def __init__(self, enable=True):
+        self.enable = enable
+
+    def __enter__(self):
+        global PARALLEL_BRANCHES
+        self.saved = PARALLEL_BRANCHES
+        if self.enable:
+            PARALLEL_BRANCHES = True
+
+    def __exit__(self, *exc):
+        global PARALLEL_BRANCHES
+        PARALLEL_BRANCHES = self.saved
+        return False
+
+
+def _each_tensor(x):
+    if isinstance(x, th.Tensor):
+        yield x
+    elif isinstance(x, (tuple, list)):
+        for y in x:
+            yield from _each_tensor(y)
+    elif isinstance(x, dict):
+        for y in x.values():
+            yield from _each_tensor(y)
+
+
+def branches(fns):
+    """Results of the independent closures `fns`, in order. With PARALLEL_BRANCHES the first runs on the current
+    stream and each other one on its own side stream forked from / joined to it."""
+    if not PARALLEL_BRANCHES or len(fns) < 2 or not th.cuda.is_available():
+        return [f() for f in fns]
+    main = th.cuda.current_stream()
+    sides = [th.cuda.Stream(device=main.device) for _ in fns[1:]]
+    out = [None] * len(fns)
+    for i, st in enumerate(sides, start=1):
+        st.wait_stream(main)
+        with th.cuda.stream(st):
+            out[i] = fns[i]()
+    out[0] = fns[0]()
+    for i, st in enumerate(sides, start=1):
+        main.wait_stream(st)
+        for t in _each_tensor(out[i]):
+            t.record_stream(main)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # row-streaming helpers (rowops.cu)
 # ------------------------------------------------------------------------------------------------
 def _rows_ok(t):
