@@ -43,12 +43,31 @@ struct LoadBF16 {
   }
 };
 
-template <typename L, int NCHUNK, int kUnroll, bool kWeighted, int kMinBlocks>
+// L2 prefetch of the 128-byte lines [first, last] of one gathered row, spread over `lanes` lanes (sub = lane's slot)
+__device__ __forceinline__ void prefetch_row_l2(const void* row, unsigned bytes, int sub, int lanes) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+  const uintptr_t first = a >> 7, last = (a + bytes - 1) >> 7;
+  for (uintptr_t ln = first + sub; ln <= last; ln += lanes)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ln << 7) : "memory");
+}
+
+// Prefetch distance in groups of kUnroll rows (0 = off). DG_SPMM_PREFETCH overrides the default for experiments.
+static int spmm_prefetch_distance() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DG_SPMM_PREFETCH");
+    v = e ? atoi(e) : 1;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
+template <typename L, int NCHUNK, int kUnroll, bool kWeighted, int kMinBlocks, bool kPf>
 __global__ void __launch_bounds__(256, kMinBlocks)
 spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ vals,
                 const float* __restrict__ src_scale, const float* __restrict__ dst_scale,
                 const float* __restrict__ bias, const typename L::Elem* __restrict__ x, int64_t ldx,
-                float* __restrict__ out, int64_t ldo, int64_t n_rows, int d, int n_slabs, int flags) {
+                float* __restrict__ out, int64_t ldo, int64_t n_rows, int d, int n_slabs, int flags, int pf_dist) {
   constexpr int V = L::kVec;
   constexpr int kSlabCols = 32 * V * NCHUNK;
   const int lane = lane_id();
@@ -57,6 +76,14 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
   if (row >= n_rows) return;
   const int slab = static_cast<int>(warp - row * n_slabs);
   const int col0 = slab * kSlabCols + lane * V;     // chunk c covers columns col0 + c*32*V .. +V
+  // L2 prefetch of the rows this warp will gather `pf_dist` groups from now (prefetch.global.L2 on each 128-byte line
+  // of the row, 32 / kUnroll lanes per row). Holds no registers and no shared memory, so the bytes in flight towards
+  // DRAM are no longer bounded by the register file; the demand loads that follow find their lines in L2.
+  const int slab_c0 = slab * kSlabCols;
+  const unsigned pf_bytes = static_cast<unsigned>((min(d, slab_c0 + kSlabCols) - slab_c0) * static_cast<int>(sizeof(typename L::Elem)));
+  const int pf_lo = pf_dist * kUnroll;               // prefetch window [t + pf_lo, t + pf_lo + kUnroll) in batch positions
+  constexpr int kPfLanes = 32 / kUnroll;             // lanes sharing one row of the window
+  const int pf_r = lane / kPfLanes, pf_sub = lane % kPfLanes;
 
   float acc[NCHUNK][V];
   bool live[NCHUNK];
@@ -93,9 +120,27 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
     }
     const int cnt = min(32, end - base);
     int t = 0;
+    if (kPf && base == beg) {
+      // start of the row: the groups 1 .. pf_dist-1 of the first batch, which no earlier window covered
+      for (int q0 = kUnroll; q0 < pf_lo; q0 += kUnroll) {
+        const int q = q0 + pf_r;
+        const int jj = __shfl_sync(kFull, j, q & 31);
+        if (q < cnt) prefetch_row_l2(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
+      }
+    }
     for (; t + kUnroll <= cnt; t += kUnroll) {
       typename L::Raw buf[kUnroll][NCHUNK];   // raw 128-bit vectors; unpacked only at FMA time
       float wt[kUnroll];
+      if (kPf) {
+        const int q = t + pf_lo + pf_r;                 // batch position of the row this lane helps to prefetch
+        if (t + pf_lo + kUnroll <= 32) {                // window inside this batch (warp-uniform branch)
+          const int jj = __shfl_sync(kFull, j, q & 31);
+          if (q < cnt) prefetch_row_l2(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
+        } else if (t + pf_lo >= 32) {                   // window inside the next batch: its indices landed long ago
+          const int jj = __shfl_sync(kFull, j_nx, (q - 32) & 31);
+          if (base + q < end) prefetch_row_l2(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
+        }
+      }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int jj = __shfl_sync(kFull, j, t + u);
@@ -170,12 +215,18 @@ static int launch_spmm(const int* indptr, const int* indices, const float* vals,
   const int64_t warps = n_rows * n_slabs;
   const int64_t blocks = (warps + 7) / 8;
   if (blocks > 0x7fffffffLL) { set_error("spmm: grid too large"); return DG_ERR_INVALID_ARGUMENT; }
-  if (vals || src_scale)
-    spmm_csr_kernel<L, NCHUNK, kUnroll, true, kMinBlocks><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
-  else
-    spmm_csr_kernel<L, NCHUNK, kUnroll, false, kMinBlocks><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-        indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
+  int pf = (flags & DG_SPMM_PREFETCH) ? spmm_prefetch_distance() : 0;
+  if (pf * kUnroll > 32 - kUnroll) pf = (32 - kUnroll) / kUnroll;      // the window stays within one batch + the next
+#define DG_SPMM_LAUNCH(W, P)                                                                                   \
+  spmm_csr_kernel<L, NCHUNK, kUnroll, W, kMinBlocks, P><<<static_cast<unsigned>(blocks), 256, 0, st>>>(          \
+      indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags, pf)
+  const bool weighted = vals || src_scale;
+  if (pf > 0) {
+    if (weighted) DG_SPMM_LAUNCH(true, true); else DG_SPMM_LAUNCH(false, true);
+  } else {
+    if (weighted) DG_SPMM_LAUNCH(true, false); else DG_SPMM_LAUNCH(false, false);
+  }
+#undef DG_SPMM_LAUNCH
   DG_CHECK_LAUNCH("spmm_csr");
   return DG_OK;
 }

@@ -108,9 +108,13 @@ DG_API int dg_csr_expand_rows(const int32_t* indptr, int64_t n_rows, int32_t* ro
  *   vals == NULL, and torch.spmm(adj, support) (+ bias, layers.py:312-314) when vals != NULL.
  *   The backward is the same call on the transposed CSR with the two scales swapped -- atomic-free
  *   and bit-reproducible. vals, src_scale, dst_scale, bias may each be NULL.
- *   flags: DG_SPMM_ACCUMULATE adds into `out`; DG_SPMM_RELU applies max(.,0) last. */
+ *   flags: DG_SPMM_ACCUMULATE adds into `out`; DG_SPMM_RELU applies max(.,0) last; DG_SPMM_PREFETCH is a
+ *   hint that the gathered operand does not stay resident in L2 (x larger than ~half of it): the kernel then
+ *   issues L2 prefetches (prefetch.global.L2) for the rows it will gather one group ahead, so the bytes in flight
+ *   towards HBM are not bounded by the registers holding demand loads. Results are identical with and without. */
 #define DG_SPMM_ACCUMULATE 1
 #define DG_SPMM_RELU 2
+#define DG_SPMM_PREFETCH 4
 DG_API int dg_spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                     const float* src_scale, const float* dst_scale, const float* bias,
                     const float* x, int64_t ldx, float* out, int64_t ldo,

@@ -481,3 +481,32 @@ def test_spmm_relu_bias_backward_fused(dev):
     assert H.rel_err(out.detach().cpu().double(), ref.detach()) <= FP32_TOL
     assert H.rel_err(x.grad.cpu().double(), xr.grad) <= FP32_TOL
     assert H.rel_err(bias.grad.cpu().double(), br.grad) <= FP32_TOL
+
+
+@pytest.mark.parametrize('d', [4, 128, 344, 768])
+@pytest.mark.parametrize('weighted', [False, True])
+def test_spmm_l2_prefetch_instance_is_bit_identical(dev, d, weighted, monkeypatch):
+    """DG_SPMM_PREFETCH only adds prefetch.global.L2 hints one group ahead of the demand loads (rows of the current
+    batch, of the next batch, start of a row): same sums in the same order, on rows of every length class."""
+    o = ops()
+    rng = np.random.default_rng(d + 7)
+    lengths = [0, 1, 3, 4, 5, 31, 32, 33, 36, 63, 64, 65, 100, 257, 1000]
+    n_rows, n_cols = len(lengths), 300
+    row = np.concatenate([np.full(n, i) for i, n in enumerate(lengths)])
+    col = rng.integers(0, n_cols, row.size)
+    val = th.tensor(rng.random(row.size).astype(np.float32), device=dev) if weighted else None
+    csr = o.CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), n_rows, n_cols, val)
+    x = th.randn(n_cols, d, device=dev)
+    ss = th.rand(n_cols, device=dev) if weighted else None
+    outs = {}
+    for on in (False, True):
+        monkeypatch.setattr(o, 'SPMM_PREFETCH_MIN_BYTES', 0 if on else 1 << 60)
+        monkeypatch.setattr(o, 'SPMM_PREFETCH_MIN_BYTES_WIDE', 0 if on else 1 << 60)
+        outs[on] = o._spmm_raw(csr, x, ss, None, None, 0)
+        outs[(on, 'bf16')] = o._spmm_raw(csr, x.to(th.bfloat16), ss, None, None, 0) if d % 8 == 0 else None
+    assert th.equal(outs[False], outs[True])
+    if d % 8 == 0:
+        assert th.equal(outs[(False, 'bf16')], outs[(True, 'bf16')])
+    want = _dense_spmm(row, col, None if val is None else val.cpu().numpy(), n_rows, x.cpu(), None if ss is None else ss.cpu(),
+                       None, None, False)
+    assert H.rel_err(outs[True].cpu(), want) <= FP32_TOL
