@@ -95,6 +95,13 @@ __device__ __forceinline__ int ldg_i32_stream(const int* p) {
   return r;
 }
 
+// 256-bit streaming store (sm_100: STG.256): one full 32-byte sector per thread
+__device__ __forceinline__ void st_global_cs_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // Counter-based dropout generator shared by forward and backward kernels: the keep decisions of the four
 // units (4g .. 4g+3) of pair / row `a` under `seed` are a pure function, so the backward regenerates the
 // forward's mask. Two rounds of a 32-bit integer hash give four 16-bit uniforms per call (one call per
