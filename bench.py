@@ -334,6 +334,15 @@ def run_b200(args):
     per_step = len(log) // max(log_steps, 1)
     spmm_ms_by_step = [round(sum(r[7].elapsed_time(r[8]) for r in log[i * per_step:(i + 1) * per_step]), 2)
                        for i in range(log_steps)] if per_step else []
+    # per-launch view (same events): launch i of a step averaged over the logged steps
+    per_launch = []
+    for i in range(per_step):
+        recs = [log[s_ * per_step + i] for s_ in range(log_steps)]
+        tag, nnz, nr, nc, d, el, valued = recs[0][:7]
+        t_ms = sum(r[7].elapsed_time(r[8]) for r in recs) / log_steps
+        per_launch.append({'tag': tag, 'rows': int(nr), 'cols': int(nc), 'nnz': int(nnz), 'd': int(d),
+                           'operand_mb': round(nc * d * el / 1e6, 1), 'ms': round(t_ms, 3),
+                           'gather_GBps': round(spmm_algorithmic_bytes(nnz, nr, nc, d, el, valued) / (t_ms / 1e3) / 1e9, 1)})
     top_key, top = max(classes.items(), key=lambda kv: kv[1]['ms'])
     peak, peak_src = measured_peak()
     achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
@@ -394,7 +403,7 @@ def run_b200(args):
                            'resident as in the reference training loop (train.py:186-200)'
                            % (', then copied device-to-device into the captured graph\'s input buffers'
                               if (args.cuda_graph and not rows) else '')},
-           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'step_ms': step_ms, 'allocator': alloc_diag, 'host_enqueue_ms': host_ms, 'spmm_ms_by_step': spmm_ms_by_step,
+           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'step_ms': step_ms, 'allocator': alloc_diag, 'host_enqueue_ms': host_ms, 'spmm_ms_by_step': spmm_ms_by_step, 'spmm_launches': per_launch,
            'final_loss': round(loss_host, 6)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

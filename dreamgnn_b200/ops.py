@@ -645,6 +645,26 @@ class LinearFunction(th.autograd.Function):
         return dx, dw, db
 
 
+class SmallLinearFunction(th.autograd.Function):
+    """y = x @ w^T + b below the tensor-core kernel's size threshold: the three GEMMs stay with the library (cuBLAS via
+    torch), the bias gradient is the deterministic one-pass column sum (autograd's dy.sum(0) is a single-CTA reduction
+    at these shapes: ~30 us on the critical path of every small layer)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return th.addmm(b, x, w.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        dw = dy.t() @ x if ctx.needs_input_grad[1] else None
+        db = colsum(dy) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
 def linear(x, w, b=None):
     """F.linear(x, w, b) for 2-D x; tcgen05 3xTF32 above GEMM_MIN_MACS, cuBLAS (torch) below."""
     if not x.is_cuda:
@@ -652,6 +672,8 @@ def linear(x, w, b=None):
     if (gemm_backend() == 'tcgen05' and x.dim() == 2 and x.dtype == th.float32 and w.dtype == th.float32
             and x.shape[0] * w.shape[0] * w.shape[1] >= GEMM_MIN_MACS):
         return LinearFunction.apply(x, w, b)
+    if b is not None and x.dim() == 2 and x.dtype == th.float32 and w.dtype == th.float32 and w.shape[0] % 4 == 0:
+        return SmallLinearFunction.apply(x, w, b)
     return th.nn.functional.linear(x, w, b)
 
 

@@ -1,19 +1,16 @@
-run() { # name, env...
+#!/bin/bash
+# A/B of the SpMM L2-prefetch switch inside the real training step (per-launch CUDA-event times of bench.py)
+run() {
   name=$1; shift
-  env "$@" python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/b_$name.json 2> gpurun_out/b_sweep.err
+  env "$@" python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/b_$name.json 2> gpurun_out/b_sweep.err
   python - "$name" <<'PY'
 import json,sys
 n=sys.argv[1]
-try:
-    d=json.load(open("gpurun_out/b_%s.json"%n))
-    print(n, d["ms_per_step"], {k:v["ms_per_step"] for k,v in d["roofline"]["all_spmm_classes"].items()})
-except Exception as e:
-    print(n, "failed", e)
+d=json.load(open("gpurun_out/b_%s.json"%n))
+print(n, d["ms_per_step"])
+for l in d["spmm_launches"]:
+    if l["ms"] > 0.3: print("   ", l)
 PY
 }
-run th120 DG_SPMM_PREFETCH_MIN_MB=120
-run th48 DG_SPMM_PREFETCH_MIN_MB=48
-run th120_v1 DG_SPMM_PREFETCH_MIN_MB=120 DG_SPMM_VARIANT=1
-run th120_v1_pf2 DG_SPMM_PREFETCH_MIN_MB=120 DG_SPMM_VARIANT=1 DG_SPMM_PREFETCH=2
-run th120_v2 DG_SPMM_PREFETCH_MIN_MB=120 DG_SPMM_VARIANT=2
-run th120_v2_pf2 DG_SPMM_PREFETCH_MIN_MB=120 DG_SPMM_VARIANT=2 DG_SPMM_PREFETCH=2
+run pf_on
+run pf_off DG_SPMM_PREFETCH_MIN_MB=100000000 DG_SPMM_PREFETCH_MIN_MB_WIDE=100000000
