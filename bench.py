@@ -401,7 +401,9 @@ def run_b200(args):
                    'what': 'features + labels copied from pinned host memory every step (next step prefetched on a side '
                            'stream while the current one computes%s), loss read back every step; graph structure stays '
                            'resident as in the reference training loop (train.py:186-200)'
-                           % (', then copied device-to-device into the captured graph\'s input buffers'
+                           % ((', then copied device-to-device into the captured graph\'s input buffers'
+                               + ('; the augmentation branch of replay i draws from them for replay i+1'
+                                  if getattr(step, 'staged', None) is not None else ''))
                               if (args.cuda_graph and not rows) else '')},
            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'step_ms': step_ms, 'allocator': alloc_diag, 'host_enqueue_ms': host_ms, 'spmm_ms_by_step': spmm_ms_by_step, 'spmm_launches': per_launch,
            'final_loss': round(loss_host, 6)}
@@ -409,7 +411,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_reference(args, steps=1, warmup=1)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -535,10 +537,28 @@ def run_reference(args):
            'cpu_baseline': base,
            'e2e': {'value': base['value'], 'unit': 'GE/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
            'gpu_launches': 0}
-    print(json.dumps(out))
+    emit(out)
+
+
+_JSON_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the process's original stdout; everything else a library prints during the run (NCCL's
+    version banner, warnings) was redirected to stderr by main()."""
+    line = (json.dumps(obj) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)            # keep the real stdout for the JSON line
+    os.dup2(2, 1)                   # any other write to fd 1 (C libraries included) lands on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)

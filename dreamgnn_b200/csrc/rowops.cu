@@ -14,7 +14,7 @@ constexpr int kColsumWarps = 8;
 
 __host__ __device__ inline int colsum_slabs(int64_t n_rows, int64_t d) {
   const int chunks = static_cast<int>((d + kColChunk - 1) / kColChunk);
-  int64_t s = (4 * kNumSM + chunks - 1) / chunks;                       // ~4 CTAs per SM over all chunks
+  int64_t s = (2 * kNumSM + chunks - 1) / chunks;                       // ~2 CTAs per SM over all chunks
   const int64_t max_s = (n_rows + kColsumWarps - 1) / kColsumWarps;      // at least one row per warp
   if (s > max_s) s = max_s;
   if (s < 1) s = 1;
@@ -81,12 +81,12 @@ colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, const float* __r
   }
 }
 
-// out[col] = sum of the slab partials in a fixed order: 8 warps each sum a contiguous range of slabs for 32 columns
-// (independent loads, double accumulators), then the 8 range sums are added in range order.
-constexpr int kFinishGroups = 8;
+// out[col] = sum of the slab partials in a fixed order: 32 warps each sum a contiguous range of slabs for 32 columns
+// (every load independent, double accumulators), then the 32 range sums are added in range order.
+constexpr int kFinishGroups = 32;
 __global__ void __launch_bounds__(32 * kFinishGroups)
 colsum_finish_kernel(const float* __restrict__ partial, int slabs, int d, float* __restrict__ out) {
-  __shared__ double red[kFinishGroups][32];
+  __shared__ double red[kFinishGroups][33];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
   const int per = (slabs + kFinishGroups - 1) / kFinishGroups;

@@ -138,6 +138,8 @@ if os.path.isfile(path):
     shutil.copy(path, os.path.join(P, 'r01b_launches_syn20m_step.csv'))
 for src, dst in (('bench_lrssl_b.json', 'r01b_bench_lrssl.json'), ('bench_gdataset_b.json', 'r01b_bench_gdataset.json'),
                  ('bench_cdataset_b.json', 'r01b_bench_cdataset.json'), ('bench_folds_2gpu_b.json', 'r01b_bench_syn20m_folds_2gpu.json'),
-                 ('bench_reference_b.json', 'r01b_bench_reference_arm.json')):
+                 ('bench_rows_2gpu_b.json', 'r01b_bench_syn20m_rows_2gpu.json'), ('bench_reference_b.json', 'r01b_bench_reference_arm.json')):
     if os.path.isfile(os.path.join(G, src)):
-        shutil.copy(os.path.join(G, src), os.path.join(P, dst))
+        lines = [ln for ln in open(os.path.join(G, src)).read().splitlines() if ln.startswith('{')]
+        if lines:
+            open(os.path.join(P, dst), 'w').write(lines[-1] + '\n')        # the JSON line only (NCCL banner dropped)
