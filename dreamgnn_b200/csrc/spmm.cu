@@ -206,6 +206,125 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
   }
 }
 
+// ---- row-split variant for graphs with FEW, LONG rows (the real datasets: ~700 rows of ~600 edges) ---------------
+// One CTA per (row, slab): its 8 warps take contiguous eighths of the row's 32-edge batches, accumulate exactly like
+// the warp-per-row kernel, and warp 0 adds the eight partial rows in warp order (fixed order: bit-reproducible) before
+// the same epilogue. 8x the parallelism when warp-per-row would leave most of the 148 SMs idle.
+template <typename L, int NCHUNK, int kUnroll, bool kWeighted>
+__global__ void __launch_bounds__(256)
+spmm_csr_rowsplit_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ vals,
+                         const float* __restrict__ src_scale, const float* __restrict__ dst_scale,
+                         const float* __restrict__ bias, const typename L::Elem* __restrict__ x, int64_t ldx,
+                         float* __restrict__ out, int64_t ldo, int64_t n_rows, int d, int n_slabs, int flags) {
+  constexpr int V = L::kVec;
+  constexpr int kSlabCols = 32 * V * NCHUNK;
+  constexpr int kWarps = 8;
+  __shared__ float red[kWarps - 1][NCHUNK][V][32];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x / n_slabs;
+  const int slab = static_cast<int>(blockIdx.x - row * n_slabs);
+  const int col0 = slab * kSlabCols + lane * V;
+  float acc[NCHUNK][V];
+  bool live[NCHUNK];
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    live[c] = col0 + c * 32 * V < d;
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[c][v] = 0.f;
+  }
+  const int rbeg = indptr[row], rend = indptr[row + 1];
+  const int nb = (rend - rbeg + 31) >> 5;                       // 32-edge batches of the row
+  const int beg = rbeg + ((nb * warp) / kWarps) * 32;
+  const int end = min(rend, rbeg + ((nb * (warp + 1)) / kWarps) * 32);
+  for (int base = beg; base < end; base += 32) {
+    const int cnt = min(32, end - base);
+    int j = 0;
+    float w = 0.f;
+    if (lane < cnt) {
+      j = ldg_i32_stream(indices + base + lane);
+      if (kWeighted) w = (vals ? vals[base + lane] : 1.f) * (src_scale ? src_scale[j] : 1.f);
+    }
+    int t = 0;
+    for (; t + kUnroll <= cnt; t += kUnroll) {
+      typename L::Raw buf[kUnroll][NCHUNK];
+      float wt[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int jj = __shfl_sync(kFull, j, t + u);
+        const typename L::Elem* xr = x + static_cast<int64_t>(jj) * ldx + col0;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+          if (live[c]) buf[u][c] = L::load(xr + c * 32 * V);
+      }
+      if (kWeighted) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) wt[u] = __shfl_sync(kFull, w, t + u);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+          if (live[c]) {
+            float b[V];
+            L::unpack(buf[u][c], b);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[c][v] = kWeighted ? fmaf(wt[u], b[v], acc[c][v]) : acc[c][v] + b[v];
+          }
+    }
+    for (; t < cnt; ++t) {
+      const int jj = __shfl_sync(kFull, j, t);
+      const float wt = kWeighted ? __shfl_sync(kFull, w, t) : 1.f;
+      const typename L::Elem* xr = x + static_cast<int64_t>(jj) * ldx + col0;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c)
+        if (live[c]) {
+          float b[V];
+          L::unpack(L::load(xr + c * 32 * V), b);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[c][v] = kWeighted ? fmaf(wt, b[v], acc[c][v]) : acc[c][v] + b[v];
+        }
+    }
+  }
+  if (warp > 0) {
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+      for (int v = 0; v < V; ++v) red[warp - 1][c][v][lane] = acc[c][v];
+  }
+  __syncthreads();
+  if (warp != 0) return;
+#pragma unroll
+  for (int wq = 0; wq < kWarps - 1; ++wq)                       // fixed order: warp 0 + warp 1 + ... + warp 7
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c)
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[c][v] += red[wq][c][v][lane];
+  const float ds = dst_scale ? dst_scale[row] : 1.f;
+  float* orow = out + row * ldo;
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    if (!live[c]) continue;
+    const int col = col0 + c * 32 * V;
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) {
+      float4 r = make_float4(acc[c][4 * q] * ds, acc[c][4 * q + 1] * ds, acc[c][4 * q + 2] * ds, acc[c][4 * q + 3] * ds);
+      if (bias) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + col + 4 * q);
+        r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+      }
+      float4* op = reinterpret_cast<float4*>(orow + col + 4 * q);
+      if (flags & DG_SPMM_ACCUMULATE) {
+        const float4 o = *op;
+        r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+      }
+      if (flags & DG_SPMM_RELU) {
+        r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+      }
+      *op = r;
+    }
+  }
+}
+
 template <typename L, int NCHUNK, int kUnroll, int kMinBlocks>
 static int launch_spmm(const int* indptr, const int* indices, const float* vals, const float* src_scale,
                        const float* dst_scale, const float* bias, const typename L::Elem* x, int64_t ldx, float* out,
@@ -213,6 +332,17 @@ static int launch_spmm(const int* indptr, const int* indices, const float* vals,
   constexpr int kSlabCols = 32 * L::kVec * NCHUNK;
   const int n_slabs = (d + kSlabCols - 1) / kSlabCols;
   const int64_t warps = n_rows * n_slabs;
+  if (flags & DG_SPMM_ROWSPLIT) {
+    if (warps > 0x7fffffffLL) { set_error("spmm: grid too large"); return DG_ERR_INVALID_ARGUMENT; }
+    if (vals || src_scale)
+      spmm_csr_rowsplit_kernel<L, NCHUNK, kUnroll, true><<<static_cast<unsigned>(warps), 256, 0, st>>>(
+          indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
+    else
+      spmm_csr_rowsplit_kernel<L, NCHUNK, kUnroll, false><<<static_cast<unsigned>(warps), 256, 0, st>>>(
+          indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
+    DG_CHECK_LAUNCH("spmm_csr_rowsplit");
+    return DG_OK;
+  }
   const int64_t blocks = (warps + 7) / 8;
   if (blocks > 0x7fffffffLL) { set_error("spmm: grid too large"); return DG_ERR_INVALID_ARGUMENT; }
   int pf = (flags & DG_SPMM_PREFETCH) ? spmm_prefetch_distance() : 0;

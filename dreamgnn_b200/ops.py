@@ -18,7 +18,9 @@ from . import _lib as L
 
 I32 = th.int32
 DEC_H1, DEC_H2 = 128, 64
-SPMM_ACCUMULATE, SPMM_RELU, SPMM_PREFETCH = 1, 2, 4
+SPMM_ACCUMULATE, SPMM_RELU, SPMM_PREFETCH, SPMM_ROWSPLIT = 1, 2, 4, 8
+# few, long rows: CTA per row instead of warp per row (148 SMs x 16 resident warps want >= ~2400 rows otherwise)
+SPMM_ROWSPLIT_MAX_ROWS, SPMM_ROWSPLIT_MIN_AVG_LEN = 2368, 128
 # Gathered operands that do not stay resident in L2 (126 MB, shared with the index and output streams): the SpMM then
 # prefetches the rows it is about to gather into L2 one group ahead (DG_SPMM_PREFETCH flag of the C ABI). Measured at
 # syn20m: d=344 launches -22 %, d=768 -16 %, the decoder's segment sums -10 %; L2-resident launches of narrow rows
@@ -341,6 +343,8 @@ def _spmm_raw(csr, x, src_scale=None, dst_scale=None, bias=None, flags=0, out=No
     for nm, t, n in (('src_scale', src_scale, csr.n_cols), ('dst_scale', dst_scale, csr.n_rows), ('bias', bias, d)):
         if t is not None and (t.numel() != n or t.dtype != th.float32):
             raise ValueError('spmm: %s must be fp32 with %d elements' % (nm, n))
+    if 0 < csr.n_rows <= SPMM_ROWSPLIT_MAX_ROWS and csr.nnz >= SPMM_ROWSPLIT_MIN_AVG_LEN * csr.n_rows:
+        flags |= SPMM_ROWSPLIT
     operand = csr.n_cols * d * x.element_size()
     if operand >= SPMM_PREFETCH_MIN_BYTES or (d * x.element_size() >= 1024 and operand >= SPMM_PREFETCH_MIN_BYTES_WIDE):
         flags |= SPMM_PREFETCH

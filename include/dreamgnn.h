@@ -115,6 +115,10 @@ DG_API int dg_csr_expand_rows(const int32_t* indptr, int64_t n_rows, int32_t* ro
 #define DG_SPMM_ACCUMULATE 1
 #define DG_SPMM_RELU 2
 #define DG_SPMM_PREFETCH 4
+/* DG_SPMM_ROWSPLIT: few, long rows (the real datasets: ~700 rows of ~600 edges) -- one CTA per row whose 8 warps take
+ * contiguous eighths of the row and are summed in warp order (deterministic; the rounding order differs from the
+ * warp-per-row kernel's). The host sets it when warp-per-row would leave most SMs idle. */
+#define DG_SPMM_ROWSPLIT 8
 DG_API int dg_spmm_csr_f32(const int32_t* indptr, const int32_t* indices, const float* vals,
                     const float* src_scale, const float* dst_scale, const float* bias,
                     const float* x, int64_t ldx, float* out, int64_t ldo,
