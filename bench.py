@@ -178,7 +178,7 @@ def run_b200(args):
             eager_launches = _lib.launch_count()
             step = GraphedIteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs,
                                     pipeline_aug=False if args.serial_aug else (True if args.pipeline_aug else None),
-                                    parallel_routes=False if args.serial_aug else None)
+                                    parallel_routes=True if args.parallel_routes else (False if args.serial_aug else None))
     del w
 
     def barrier():
@@ -573,6 +573,8 @@ def main():
                     help='CUDA-graph mode: keep the augmentation inside its own iteration (default: by size -- at the small '
                          'real-dataset shapes the draw for iteration i+1 runs on a second stream beside iteration i)')
     ap.add_argument('--pipeline-aug', action='store_true', help='force the pipelined augmentation at any size')
+    ap.add_argument('--parallel-routes', action='store_true',
+                    help='force the GCMC / FGCN routes (and the per-node-type halves) onto parallel graph branches at any size')
     ap.add_argument('--cuda-graph', action='store_true',
                     help='replay the whole training iteration from one captured CUDA graph (launch-bound small shapes)')
     ap.add_argument('--messages', default='f32', choices=['f32', 'bf16'],
