@@ -246,7 +246,7 @@ def run_b200(args):
         # the graph replays carry no per-kernel events: the per-launch SpMM durations behind `roofline` come from
         # eager steps of the same iteration run right here (CUDA events around every SpMM launch on its stream),
         # while the clock sampler is still running
-        launches = eager_launches * args.steps
+        launches = getattr(step, 'launches_per_replay', eager_launches) * args.steps       # kernels recorded into the graph
         log_steps = min(3, args.steps)
         ops.PROFILE = []
         for _ in range(log_steps):

@@ -27,6 +27,8 @@ _SIGNATURES = {
     'dg_csr_build': (c_int, [_P, _P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     'dg_degree_norm': (c_int, [_P, c_int64, _P, _P]),
     'dg_keep_flags_from_perm': (c_int, [_P, c_int64, c_int64, _P, _P]),
+    'dg_random_subset_workspace_bytes': (c_size_t, []),
+    'dg_random_subset_flags': (c_int, [_P, c_int64, c_int64, _P, _P, c_size_t, _P]),
     'dg_csr_compact_workspace_bytes': (c_size_t, [c_int64]),
     'dg_csr_compact': (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     'dg_csr_expand_rows': (c_int, [_P, c_int64, _P, _P]),

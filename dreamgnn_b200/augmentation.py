@@ -14,6 +14,8 @@ Differences that are deliberate (documented in DESIGN.md):
   * failures raise instead of being printed and swallowed (augmentation.py:446-447 etc.);
   * add_random_edges draws candidates with torch's device generator, not Python's `random`.
 """
+import os
+
 import numpy as np
 import torch as th
 
@@ -28,9 +30,19 @@ def num_keep_edges(num_edges, dropout_rate):
 
 
 def _randperm(n, device):
-    """th.randperm on the graph's device (augmentation.py:51, :117). Under CUDA-graph capture torch's small-n
-    path (n < 30000 is drawn on the CPU and copied) cannot be recorded, so a random-key argsort stands in."""
-    if n < 30000 and th.device(device).type == 'cuda' and th.cuda.is_current_stream_capturing():
+    """The random order whose first `num_keep` entries are kept (augmentation.py:51, :117).
+
+    Eager: `th.randperm` on the graph's device, exactly as the reference -- the kept sets are the reference's for a
+    given generator state. Inside a CUDA-graph capture (where the generator's offsets already differ from an eager
+    run, and torch's small-n randperm, drawn on the CPU, cannot be recorded at all) only the kept SET is needed: an
+    `ops.RandomSubset` marker makes `ops.keep_flags` draw a uniformly random num_keep-subset with a sort-free radix
+    select -- the same distribution as randperm[:num_keep]. DG_EDGE_SAMPLER=randperm / select forces either."""
+    mode = os.environ.get('DG_EDGE_SAMPLER', 'auto')
+    on_cuda = th.device(device).type == 'cuda'
+    capturing = on_cuda and th.cuda.is_current_stream_capturing()
+    if on_cuda and (mode == 'select' or (mode == 'auto' and capturing)):
+        return ops.RandomSubset(n)
+    if n < 30000 and capturing:
         return th.argsort(th.rand(n, device=device))
     return th.randperm(n, device=device)
 

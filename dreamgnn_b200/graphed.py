@@ -180,6 +180,8 @@ class GraphedIteration:
             th.cuda.synchronize()
         self.graph = th.cuda.CUDAGraph()
         optimizer.zero_grad(set_to_none=True)
+        from . import _lib
+        launches0 = _lib.launch_count()
         with th.cuda.graph(self.graph):
             if self.staged is None:
                 self.loss = self._step()
@@ -194,6 +196,7 @@ class GraphedIteration:
                 main.wait_stream(self._aug_stream)                       # join
         if hasattr(model, 'parallel_routes'):
             model.parallel_routes = False                                # the branches are in the graph; eager calls stay serial
+        self.launches_per_replay = _lib.launch_count() - launches0       # C-ABI kernels recorded into the graph
 
     def __call__(self):
         """Run one iteration; returns the (static) device tensor holding its loss."""

@@ -140,12 +140,35 @@ class CSR:
         return out
 
 
+class RandomSubset:
+    """Stands in for a permutation in `keep_flags`: "a uniformly random subset of `num_keep` of these `n` edges", drawn
+    by the sort-free radix select of `dg_random_subset_flags` when the flags are built."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+
+def random_subset_flags(n, num_keep, out, rnd=None):
+    """out[i] = 1 for a uniformly random `num_keep`-subset of range(n) (uint8 [n], contiguous); graph-capturable.
+    `rnd` (int64 [n], 63 random bits each) defaults to a fresh draw from torch's generator."""
+    lib = L.load()
+    if rnd is None:
+        rnd = th.empty(n, dtype=th.int64, device=out.device).random_()
+    ws = L.workspace(lib.dg_random_subset_workspace_bytes(), out.device)
+    L.check(lib.dg_random_subset_flags(L.ptr(rnd, th.int64, 'rnd'), int(n), int(num_keep), L.ptr(out, th.uint8, 'flags'),
+                                       L.ptr(ws), ws.numel(), L.stream()), 'random_subset_flags')
+    return out
+
+
 def keep_flags(n_edges, perms, device):
-    """uint8 keep flag per edge id: perms = [(perm int64, num_keep, id offset), ...]
+    """uint8 keep flag per edge id: perms = [(perm int64 | RandomSubset, num_keep, id offset), ...]
     (augmentation.py:48-52: keep the first num_keep entries of each randperm)."""
     lib = L.load()
     flags = th.zeros(n_edges, dtype=th.uint8, device=device)
     for perm, num_keep, offset in perms:
+        if isinstance(perm, RandomSubset):
+            random_subset_flags(perm.n, num_keep, flags[int(offset):int(offset) + perm.n])
+            continue
         L.check(lib.dg_keep_flags_from_perm(L.ptr(perm, th.int64, 'perm'), int(num_keep), int(offset), L.ptr(flags),
                                             L.stream()), 'keep_flags')
     return flags

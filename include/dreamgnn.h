@@ -90,6 +90,16 @@ DG_API int dg_degree_norm(const int32_t* indptr, int64_t n_rows, float* norm, dg
 DG_API int dg_keep_flags_from_perm(const int64_t* perm, int64_t num_keep, int64_t offset,
                             uint8_t* flags, dg_stream_t stream);
 
+/* Uniform random num_keep-subset of n edges as a flag array, without a sort: flags[i] = 1 for the num_keep smallest of the
+ * keys (rnd[i] << bits(n-1)) | i, found by an 8-pass radix SELECT (histogram + pick per digit). rnd = n random int64 drawn
+ * by the caller (63 random bits each, e.g. torch's Tensor.random_()). Same distribution as "the first num_keep entries of a
+ * random permutation" (augmentation.py:48-52, :113-118) at 9 streaming reads of rnd instead of a 7-pass radix sort of
+ * (key, index) pairs. Used inside captured CUDA graphs; the eager path keeps th.randperm + dg_keep_flags_from_perm, whose
+ * kept sets are the reference's for a given generator state. Exactly num_keep flags are set (keys are distinct). */
+DG_API size_t dg_random_subset_workspace_bytes(void);
+DG_API int dg_random_subset_flags(const int64_t* rnd, int64_t n, int64_t num_keep, uint8_t* flags, void* workspace,
+                                  size_t workspace_bytes, dg_stream_t stream);
+
 /* Compact a canonical CSR to the edges whose flag (indexed by eid) is set, preserving order, so
  * the dropped graph's CSR is again canonical without a sort. vals / out_vals may be NULL.
  * out_indices / out_eid / out_vals must hold the number of kept edges (known to the caller). */

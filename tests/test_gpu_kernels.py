@@ -550,3 +550,72 @@ def test_spmm_rowsplit_instance(dev, d, weighted, monkeypatch):
     monkeypatch.setattr(o, 'SPMM_ROWSPLIT_MAX_ROWS', 0)
     out3 = o.spmm(csr, xg.detach(), ss.to(dev), ds.to(dev), bg.detach(), relu=True)
     assert H.rel_err(out3.cpu(), out.detach().cpu()) <= 5e-6
+
+
+# ---- sort-free edge-dropout sampler (select.cu) -----------------------------------------------------------
+@pytest.mark.parametrize('n', [1, 2, 5, 257, 100003, 3_000_000])
+def test_random_subset_flags_is_the_k_smallest_keys(dev, n):
+    """dg_random_subset_flags keeps exactly the num_keep smallest of the keys (rnd << bits(n-1)) | i -- the set a full
+    sort of those keys would put first (what randperm[:num_keep] does with torch's keys)."""
+    o = ops()
+    rng = np.random.default_rng(n)
+    rnd = rng.integers(0, 2 ** 63 - 1, size=n, dtype=np.int64)
+    if n > 100:
+        rnd[::7] = rnd[3]                                   # many equal random parts: the index bits break the ties
+    bits = 0
+    while (1 << bits) < n:
+        bits += 1
+    key = (rnd.astype(np.uint64) << np.uint64(bits)) | np.arange(n, dtype=np.uint64)
+    order = np.argsort(key, kind='stable')
+    for k in sorted({0, 1, n // 3, n - 1, n} & set(range(n + 1))):
+        flags = th.zeros(n, dtype=th.uint8, device=dev)
+        o.random_subset_flags(n, k, flags, rnd=th.tensor(rnd, device=dev))
+        want = np.zeros(n, dtype=np.uint8)
+        want[order[:k]] = 1
+        np.testing.assert_array_equal(flags.cpu().numpy(), want)
+
+
+def test_random_subset_sampler_is_uniform_and_fresh(dev):
+    o = ops()
+    th.manual_seed(123)
+    n, k, draws = 4000, 1000, 400
+    acc = th.zeros(n, device=dev)
+    prev = None
+    for _ in range(draws):
+        f = o.keep_flags(n, [(o.RandomSubset(n), k, 0)], dev)
+        assert int(f.sum()) == k
+        assert prev is None or not th.equal(prev, f)
+        prev = f
+        acc += f.float()
+    freq = (acc / draws).cpu().numpy()
+    # every edge is kept with probability k/n = 0.25: binomial std 0.0217 per edge over 400 draws
+    assert abs(freq.mean() - 0.25) < 1e-9 and freq.std() < 0.03 and freq.min() > 0.12 and freq.max() < 0.38
+    # position-independent: first and second half of the index range are kept equally often
+    assert abs(freq[: n // 2].mean() - freq[n // 2:].mean()) < 0.005
+
+
+def test_edge_dropout_with_select_sampler(dev, monkeypatch):
+    """augment_graph_data with DG_EDGE_SAMPLER=select: same structure invariants as the randperm path (exact kept
+    counts per relation, forward / transposed blocks consistent, kept edges are a subset of the base graph)."""
+    from dreamgnn_b200 import graph_build as GB
+    from dreamgnn_b200.augmentation import GraphAugmentation, num_keep_edges
+    monkeypatch.setenv('DG_EDGE_SAMPLER', 'select')
+    rng = np.random.default_rng(4)
+    n_d, n_s, e = 300, 200, 20000
+    cells = rng.choice(n_d * n_s, size=e, replace=False)
+    pairs = (cells // n_s, cells % n_s)
+    labels = (rng.random(e) < 0.1).astype(np.float32)
+    g = GB.generate_enc_graph(pairs, labels, n_d, n_s, dev).int()
+    out = GraphAugmentation.random_edge_dropout(g, 0.1)
+    for c in g.canonical_etypes:
+        assert out.number_of_edges(c) == num_keep_edges(g.number_of_edges(c), 0.1)
+        s0, d0 = g.edges(etype=c)
+        s1, d1 = out.edges(etype=c)
+        base = set(zip(s0.cpu().tolist(), d0.cpu().tolist()))
+        kept = list(zip(s1.cpu().tolist(), d1.cpu().tolist()))
+        assert len(kept) == len(set(kept)) == out.number_of_edges(c) and set(kept) <= base
+    for dt in ('drug', 'disease'):
+        blk = out.block(dt)
+        t = blk.csr.transpose()
+        assert blk.csr.nnz == t.nnz == int(blk.csr.indptr[-1]) == int(t.indptr[-1])
+        assert th.equal(th.sort(blk.csr.eid).values, th.sort(t.eid).values)
