@@ -116,3 +116,50 @@ def test_package_has_no_oracle_dependency():
                 src = open(os.path.join(root, f)).read()
                 assert 'oracle' not in src.replace('oracle/', '').lower() or f == 'none', f
                 assert 'import dgl' not in src, f
+
+
+def test_new_ops_refuse_cpu_and_workspaces_are_host_functions(built):
+    lib = _lib.load()
+    assert lib.dg_colsum_workspace_bytes(100000, 128) >= 128 * 4
+    assert lib.dg_colsum_workspace_bytes(0, 128) > 0
+    assert lib.dg_random_subset_workspace_bytes() >= 256 * 4 + 16
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.colsum(th.randn(8, 4))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.gram_common_loss(th.randn(8, 4), th.randn(8, 4))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.linear(th.randn(8, 4), th.randn(4, 4), th.randn(4))
+    with pytest.raises(RuntimeError):
+        ops.random_subset_flags(4, 2, th.zeros(4, dtype=th.uint8), rnd=th.zeros(4, dtype=th.int64))
+
+
+def test_branches_are_plain_calls_unless_enabled():
+    """ops.branches: off by default (results in order, same stream); the context manager scopes the switch."""
+    calls = []
+    out = ops.branches([lambda: calls.append('a') or 1, lambda: calls.append('b') or 2, lambda: calls.append('c') or 3])
+    assert out == [1, 2, 3] and calls == ['a', 'b', 'c'] and ops.PARALLEL_BRANCHES is False
+    with ops.parallel_branches(True):
+        assert ops.PARALLEL_BRANCHES is True
+        with ops.parallel_branches(False):                 # False leaves the current setting alone
+            assert ops.PARALLEL_BRANCHES is True
+    assert ops.PARALLEL_BRANCHES is False
+    assert list(ops._each_tensor((th.zeros(1), [th.ones(1), {'k': th.ones(2)}], 3))).__len__() == 3
+
+
+def test_common_loss_cpu_path_is_the_reference_expression():
+    """On CPU tensors utils.common_loss is utils.py:87-95 literally (the oracle compares against it); the Gram identity
+    it is replaced by on CUDA gives the same value."""
+    from dreamgnn_b200.utils import common_loss, common_loss_dense, common_loss_gram_torch
+    gen = th.Generator().manual_seed(0)
+    a, b = th.randn(50, 8, generator=gen, dtype=th.float64), th.randn(50, 8, generator=gen, dtype=th.float64)
+    assert th.equal(common_loss(a, b), common_loss_dense(a, b))
+    assert abs(float(common_loss_gram_torch(a.float(), b.float())) - float(common_loss_dense(a, b))) <= 1e-6 * float(common_loss_dense(a, b))
+
+
+def test_edge_sampler_choice_on_cpu(monkeypatch):
+    from dreamgnn_b200.augmentation import _randperm, num_keep_edges
+    p = _randperm(10, 'cpu')
+    assert isinstance(p, th.Tensor) and sorted(p.tolist()) == list(range(10))
+    monkeypatch.setenv('DG_EDGE_SAMPLER', 'select')
+    assert isinstance(_randperm(10, 'cpu'), th.Tensor)        # the select sampler is a CUDA kernel: CPU graphs keep randperm
+    assert num_keep_edges(467641, 0.1) == int(467641 * 0.9) and num_keep_edges(1, 0.99) == 1
