@@ -29,6 +29,11 @@ def num_keep_edges(num_edges, dropout_rate):
     return max(1, int(num_edges * (1 - dropout_rate)))
 
 
+# below this the 17 small launches of the select cost more than the sort they replace (measured on the real-dataset
+# shapes: lrssl 2.46 ms / iteration with randperm, 2.64 ms with the select)
+SELECT_MIN_EDGES = 1 << 20
+
+
 def _randperm(n, device):
     """The random order whose first `num_keep` entries are kept (augmentation.py:51, :117).
 
@@ -36,11 +41,12 @@ def _randperm(n, device):
     given generator state. Inside a CUDA-graph capture (where the generator's offsets already differ from an eager
     run, and torch's small-n randperm, drawn on the CPU, cannot be recorded at all) only the kept SET is needed: an
     `ops.RandomSubset` marker makes `ops.keep_flags` draw a uniformly random num_keep-subset with a sort-free radix
-    select -- the same distribution as randperm[:num_keep]. DG_EDGE_SAMPLER=randperm / select forces either."""
+    select -- the same distribution as randperm[:num_keep] -- for relations of at least SELECT_MIN_EDGES edges.
+    DG_EDGE_SAMPLER=randperm / select forces either."""
     mode = os.environ.get('DG_EDGE_SAMPLER', 'auto')
     on_cuda = th.device(device).type == 'cuda'
     capturing = on_cuda and th.cuda.is_current_stream_capturing()
-    if on_cuda and (mode == 'select' or (mode == 'auto' and capturing)):
+    if on_cuda and (mode == 'select' or (mode == 'auto' and capturing and n >= SELECT_MIN_EDGES)):
         return ops.RandomSubset(n)
     if n < 30000 and capturing:
         return th.argsort(th.rand(n, device=device))
