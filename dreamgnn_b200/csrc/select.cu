@@ -52,21 +52,25 @@ select_hist_kernel(const long long* __restrict__ rnd, int64_t n, int idx_bits, i
   if (c) atomicAdd(&st->hist[threadIdx.x], c);
 }
 
-__global__ void select_pick_kernel(SelectState* st, int pass) {
-  __shared__ unsigned long long cum[257];
-  const int t = threadIdx.x;
-  if (t == 0) {
-    unsigned long long s = 0;
-    for (int d = 0; d < 256; ++d) { cum[d] = s; s += st->hist[d]; }
-    cum[256] = s;
+__global__ void __launch_bounds__(256) select_pick_kernel(SelectState* st, int pass) {
+  __shared__ unsigned long long wsum[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned long long mine_cnt = st->hist[t];
+  unsigned long long incl = mine_cnt;                          // inclusive scan of the 256 bins: warp shuffles + 8 warp sums
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long up = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += up;
   }
+  if (lane == 31) wsum[warp] = incl;
   __syncthreads();
+  for (int w = 0; w < warp; ++w) incl += wsum[w];
+  const unsigned long long excl = incl - mine_cnt;
   const unsigned long long k = st->k_rem;
-  const bool mine = cum[t] < k && k <= cum[t + 1];            // exactly one digit satisfies this (k <= total)
-  __syncthreads();
-  if (mine) {
+  __syncthreads();                                            // everyone has read k_rem before the owner rewrites it
+  if (excl < k && k <= incl) {                                // exactly one digit satisfies this (k <= total)
     st->prefix |= static_cast<unsigned long long>(t) << (56 - 8 * pass);
-    st->k_rem = k - cum[t];
+    st->k_rem = k - excl;
   }
   st->hist[t] = 0;                                            // ready for the next pass
 }

@@ -118,8 +118,9 @@ if os.path.isfile(path):
         d[1] += ms_of(row['Metric Value'], row['Metric Unit'])
         n += 1
     total = sum(v[1] for v in tot.values())
-    own = sum(v[1] for k, v in tot.items() if not k.startswith(('native', 'at_cuda', 'cutlass', 'cublas', 'elementwise', 'randperm',
-                                                               'std::', 'epilogue', 'internal')))
+    OWN = ('spmm_csr', 'gemm_nt', 'decoder_', 'colsum_', 'compact_', 'splitk_', 'select_', 'keep_flags', 'center_normalize',
+           'scan_', 'expand_rows', 'pack_rows', 'csr_', 'sort_', 'knn_', 'topk_', 'degree_')
+    own = sum(v[1] for k, v in tot.items() if k.startswith(OWN))
     bench = {}
     bp = os.path.join(G, 'bench_final_b.json')
     if os.path.isfile(bp):
