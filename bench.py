@@ -99,6 +99,17 @@ class ClockSampler:
                 'reasons': sorted(self.reasons), 'samples': len(sm)}
 
 
+def edge_sampler_label(args, state):
+    """Which sampler draws the edge dropout of the timed iterations (dreamgnn_b200.augmentation._randperm)."""
+    from dreamgnn_b200.augmentation import SELECT_MIN_EDGES
+    mode = os.environ.get('DG_EDGE_SAMPLER', 'auto')
+    g = getattr(state, 'enc_graph', None)
+    big = g is not None and any(g.number_of_edges(c) >= SELECT_MIN_EDGES for c in g.canonical_etypes)
+    if mode == 'select' or (mode == 'auto' and args.cuda_graph and big):
+        return 'uniform random k-subset by radix select (dg_random_subset_flags) for relations of >= %d edges' % SELECT_MIN_EDGES
+    return 'th.randperm (reference-exact kept sets)'
+
+
 def spmm_algorithmic_bytes(nnz, n_rows, n_cols, d, elem, valued):
     """SURVEY.md 8d gather model, the per-unit figure of the roofline: every stored edge reads its column
     index (+ value) and one d-wide source row; every output row is written once; indptr and the two
@@ -390,9 +401,7 @@ def run_b200(args):
                       'l2': 'inputs larger than L2 (gathered operand %.0f MB, indices %.0f MB per SpMM)'
                             % (top['bmin'] / top['n'] / 1e6, top['nnz'] / top['n'] * 4 / 1e6)
                             if top['bmin'] / top['n'] > 126e6 else 'working set fits L2; no flush between steps',
-                      'edge_sampler': ('uniform random k-subset by radix select (dg_random_subset_flags)'
-                                       if (args.cuda_graph or os.environ.get('DG_EDGE_SAMPLER') == 'select') else
-                                       'th.randperm (reference-exact kept sets)'),
+                      'edge_sampler': edge_sampler_label(args, state),
                       'parallelism': ('1-D row partition, NCCL all-gather of node rows per aggregation' if rows else
                                       'fold-replica per GPU, no collective') if world > 1 else 'single GPU',
                       'common_loss': 'N x N (reference form)' if spec['kind'] == 'dense' else
