@@ -103,8 +103,11 @@ def edge_sampler_label(args, state):
     """Which sampler draws the edge dropout of the timed iterations (dreamgnn_b200.augmentation._randperm)."""
     from dreamgnn_b200.augmentation import SELECT_MIN_EDGES
     mode = os.environ.get('DG_EDGE_SAMPLER', 'auto')
-    g = getattr(state, 'enc_graph', None)
-    big = g is not None and any(g.number_of_edges(c) >= SELECT_MIN_EDGES for c in g.canonical_etypes)
+    try:
+        g = state.enc_graph
+        big = any(g.number_of_edges(c) >= SELECT_MIN_EDGES for c in g.canonical_etypes)
+    except AttributeError:                                   # row-partitioned state: per-rank blocks, eager launches
+        big = False
     if mode == 'select' or (mode == 'auto' and args.cuda_graph and big):
         return 'uniform random k-subset by radix select (dg_random_subset_flags) for relations of >= %d edges' % SELECT_MIN_EDGES
     return 'th.randperm (reference-exact kept sets)'
