@@ -29,8 +29,9 @@ def num_keep_edges(num_edges, dropout_rate):
     return max(1, int(num_edges * (1 - dropout_rate)))
 
 
-# below this the 17 small launches of the select cost more than the sort they replace (measured on the real-dataset
-# shapes: lrssl 2.46 ms / iteration with randperm, 2.64 ms with the select)
+# below this the select buys nothing measurable: its 17 small launches against a sort of a few hundred thousand pairs
+# (A/B on one box: lrssl 2.46 ms / iteration with randperm vs 2.64 with the select, Gdataset 1.93 vs 1.79 -- inside the
+# run-to-run spread of these latency-chain iterations), so the sampler whose kept sets match the reference's stays
 SELECT_MIN_EDGES = 1 << 20
 
 
