@@ -11,7 +11,7 @@ import torch as th
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'lib', 'libdreamgnn.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _P = c_void_p
 _SIGNATURES = {
@@ -50,6 +50,7 @@ _SIGNATURES = {
     'dg_topk_rows_f64': (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P]),
     'dg_knn_graph_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'dg_knn_graph_from_neighbors': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'dg_bench_read_rows': (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

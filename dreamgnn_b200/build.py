@@ -66,7 +66,11 @@ def build(force=False, verbose=False):
                 raise RuntimeError('nvcc failed on %s' % src)
             objs.append(obj)
     cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIB_PATH, *objs,
-           '-Xlinker', '--no-undefined', '-lcudart_static', '-ldl', '-lrt', '-lpthread']
+           '-Xlinker', '--no-undefined', '-cudart', 'shared', '-Xlinker', '-rpath,/usr/local/cuda/lib64',
+           '-ldl', '-lrt', '-lpthread']
+    # the SHARED CUDA runtime: inside a torch process libcudart.so.12 is already loaded (torch's own copy) and is the
+    # one the loader binds; the rpath covers a plain C host. (A static runtime would embed its whole API name table
+    # in the artefact that ships to the GPU box.)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

@@ -1,0 +1,63 @@
+// Read-bandwidth microbenchmark behind profiles/l2_peak.json (scripts/l2_peak.py): the denominators of the SpMM
+// roofline. The SpMM kernels are row gathers served partly by L2, so next to the HBM copy peak of MEASURED_PEAKS.json
+// the repo measures, with the SAME load instruction and access shape the SpMM uses (one warp per row, 128-bit
+// ld.global.nc.L1::no_allocate per lane, several rows in flight per warp):
+//   * sequential rows over a buffer that fits L2      -> L2 -> SM streaming bandwidth
+//   * pseudo-random rows over a buffer that fits L2   -> L2 -> SM gather bandwidth at a given row width
+//   * the same over a buffer much larger than L2      -> HBM gather bandwidth at that row width
+#include "common.cuh"
+
+namespace dg {
+namespace {
+
+constexpr int kBenchThreads = 256;
+constexpr int kInFlight = 4;                    // rows in flight per warp (the SpMM instances keep 3-4)
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(kBenchThreads)
+bench_read_kernel(const float4* __restrict__ buf, int64_t n_rows, int row_f4, int64_t rows_per_warp, int random,
+                  float* __restrict__ sink) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kBenchThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * kBenchThreads) >> 5;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = 0; i < rows_per_warp; i += kInFlight) {
+    int64_t row[kInFlight];
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const int64_t k = i + u;
+      row[u] = random ? static_cast<int64_t>(mix32(static_cast<uint32_t>(warp * 0x9e3779b1u) ^ mix32(static_cast<uint32_t>(k)))) % n_rows
+                      : (k * n_warps + warp) % n_rows;
+    }
+    for (int c = lane; c < row_f4; c += 32) {
+      float4 v[kInFlight];
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u) v[u] = ldg_f4_stream(buf + row[u] * row_f4 + c);
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 1234.5678f) sink[0] = acc.x;       // keeps the loads alive
+}
+
+}  // namespace
+}  // namespace dg
+
+extern "C" int dg_bench_read_rows(const float* buf, int64_t n_rows, int64_t row_floats, int64_t rows_per_warp, int random,
+                                  int ctas_per_sm, float* sink, dg_stream_t stream) {
+  using namespace dg;
+  DG_REQUIRE(buf != nullptr && sink != nullptr, "null pointer");
+  DG_REQUIRE(n_rows > 0 && row_floats > 0 && row_floats % 4 == 0 && rows_per_warp > 0, "bad shape");
+  DG_REQUIRE(rows_per_warp % kInFlight == 0, "rows_per_warp must be a multiple of 4");
+  DG_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 8, "ctas_per_sm out of range");
+  bench_read_kernel<<<kNumSM * ctas_per_sm, kBenchThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(buf), n_rows, static_cast<int>(row_floats / 4), rows_per_warp, random, sink);
+  DG_CHECK_LAUNCH("bench_read_rows");
+  return DG_OK;
+}

@@ -44,7 +44,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
   return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int* __restrict__ in, int64_t n,
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int* in, int64_t n,
                                                                int* __restrict__ tile_sums) {
   int64_t base = static_cast<int64_t>(blockIdx.x) * kScanTile;
   int s = 0;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(1024) scan_spine(int* __restrict__ tile_sums, 
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tiles(const int* __restrict__ in, int* __restrict__ out,
+__global__ void __launch_bounds__(kScanThreads) scan_tiles(const int* in, int* out,   // may alias (in-place scan)
                                                            int64_t n, const int* __restrict__ tile_offsets) {
   // Each thread owns kScanItems CONSECUTIVE items so the prefix is a plain running sum.
   int64_t base = static_cast<int64_t>(blockIdx.x) * kScanTile + static_cast<int64_t>(threadIdx.x) * kScanItems;

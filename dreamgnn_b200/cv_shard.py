@@ -16,6 +16,14 @@ import torch as th
 import torch.distributed as dist
 
 
+def job_seed(seed, fold):
+    """RNG seed of one (seed, fold) job. The reference seeds once per experiment and lets the generators run on through
+    the 10 folds (train.py:471-505), which a sharded run cannot replay; here fold 0 starts from `setup_seed(seed)` exactly
+    as the reference's first fold does, and every later fold from its own deterministic seed, so no two folds of a seed
+    share initial weights or dropout / augmentation streams, on any rank count."""
+    return int(seed) if fold == 0 else (int(seed) * 1000003 + int(fold)) % (2 ** 31 - 1)
+
+
 def job_list(seeds, n_folds):
     return [(s, f) for s in seeds for f in range(n_folds)]
 
@@ -104,12 +112,15 @@ def main(argv=None):
     args.device = 'cuda:%d' % local
     if world > 1:
         dist.init_process_group('nccl', device_id=th.device(args.device))
-    # KFold uses a fixed random_state, so folds are identical across seeds: build the loader once per process
+    # KFold uses a fixed random_state, so folds are identical across seeds: build the loader once per process. Seed
+    # first (the reference seeds before it builds its loader, train.py:471-476): a `.mat` without drug_embed /
+    # disease_embed falls back to np.random embeddings, which must be the same on every rank and every run.
+    setup_seed(args.seeds[0])
     dataset = DrugDataLoader(args.data_name, args.device, symm=args.gcn_agg_norm_symm, k=args.num_neighbor,
                              use_augmentation=args.use_augmentation, n_folds=args.folds)
 
     def run_job(seed, fold):
-        setup_seed(seed)
+        setup_seed(job_seed(seed, fold))
         args.save_dir = os.path.join('seed_experiments', 'seed_%d' % seed)
         os.makedirs(args.save_dir, exist_ok=True)
         args.save_id = fold + 1

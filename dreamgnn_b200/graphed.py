@@ -151,7 +151,8 @@ class GraphedIteration:
         side = th.cuda.Stream()
         side.wait_stream(th.cuda.current_stream())
         with th.cuda.stream(side):                       # eager warm-up: builds every cached CSR, cuBLAS handles, ...
-            for _ in range(max(warmup, 1)):              # at least one eager iteration: lazy caches must exist before capture
+            self.eager_iterations = max(warmup, 1)       # at least one: lazy caches must exist before capture
+            for _ in range(self.eager_iterations):
                 self._step()
         th.cuda.current_stream().wait_stream(side)
         th.cuda.synchronize()

@@ -538,6 +538,22 @@ class DecoderFunction(th.autograd.Function):
         return dpd, dps, dw2, db2, dw3, db3, None, None, None, None
 
 
+def decoder_saved_mask(out):
+    """Diagnostic: the hidden-2 ReLU mask the backward of `out = decoder_mlp(...)` will differentiate through, as one
+    int64 per pair (bit j <=> z2[e, j] > 0), read from the state the forward saved on the autograd graph."""
+    fn = out.grad_fn
+    while fn is not None and not hasattr(fn, 'saved_tensors'):
+        fn = fn.next_functions[0][0] if fn.next_functions else None
+    if fn is None or len(fn.saved_tensors) < 5 or fn.saved_tensors[4] is None:
+        raise RuntimeError('not the output of a decoder forward that saved its state')
+    z2 = fn.saved_tensors[4]
+    bit = th.arange(DEC_H2, device=z2.device, dtype=th.int64)
+    bits = th.empty(z2.shape[0], dtype=th.int64, device=z2.device)
+    for c0 in range(0, z2.shape[0], 1 << 22):                 # chunked: the boolean / int64 temporaries are 8x z2
+        bits[c0:c0 + (1 << 22)] = ((z2[c0:c0 + (1 << 22)] > 0).to(th.int64) << bit).sum(1)
+    return bits
+
+
 def decoder_mlp(pd, ps, w2, b2, w3, b3, pairs, p=0.0, seed=0, training=False):
     if not pd.is_cuda:
         raise RuntimeError('dreamgnn_b200.decoder_mlp needs CUDA tensors (no CPU fallback)')

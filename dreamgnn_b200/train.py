@@ -153,9 +153,13 @@ def train(args, dataset, cv):
     else:
         rel_loss_fn = nn.BCEWithLogitsLoss()
     use_graph = bool(getattr(args, 'cuda_graph', False))
-    if use_graph and th.cuda.current_stream() == th.cuda.default_stream():
+    entry_stream = th.cuda.current_stream() if use_graph else None
+    if use_graph and entry_stream == th.cuda.default_stream():
         th.cuda.set_stream(th.cuda.Stream())       # graph capture cannot involve the legacy default stream
-    optimizer = th.optim.Adam(model.parameters(), lr=args.train_lr, weight_decay=args.weight_decay, capturable=use_graph)
+    # graph mode: the learning rate lives in a device tensor, which the captured Adam step reads on every replay and
+    # ReduceLROnPlateau updates in place -- a scheduler step takes effect without re-capturing
+    lr = th.tensor(float(args.train_lr), device=dev) if use_graph else args.train_lr
+    optimizer = th.optim.Adam(model.parameters(), lr=lr, weight_decay=args.weight_decay, capturable=use_graph)
     scheduler = th.optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'max', patience=500, factor=0.5)
     aug_methods = getattr(args, 'aug_methods', ['edge_dropout', 'feature_noise'])
     aug_params = aug_params_from_args(args)
@@ -165,13 +169,15 @@ def train(args, dataset, cv):
     best = dict(aupr=-1.0, auroc=0.0, it=0, train_aupr=0.0, train_auroc=0.0)
     start = time.perf_counter()
     graphed = None
+    first_it = 1
     if use_graph:
-        # the captured graph bakes the learning rate in; ReduceLROnPlateau(patience=500 evaluations) never fires
-        # within the reference's 71 evaluations per fold, so nothing is lost
         from .graphed import GraphedIteration
         graphed = GraphedIteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_params, args.beta,
                                    args.train_grad_clip, warmup=0)
-    for it in range(1, args.train_max_iter):
+        # the eager warm-up iterations before the capture are real optimiser steps: they count as training iterations,
+        # so a fold makes exactly train_max_iter - 1 updates as in the reference loop (train.py:250)
+        first_it = 1 + graphed.eager_iterations
+    for it in range(first_it, args.train_max_iter):
         if graphed is not None:
             total = graphed()
         else:
@@ -205,4 +211,6 @@ def train(args, dataset, cv):
         best_model.load_state_dict(th.load(os.path.join(args.save_dir, 'best_model_fold%s.pth' % args.save_id)))
         top = get_top_novel_predictions(args, best_model, dataset, cv, top_k=args.top_k)
         print('Top 5 novel predictions:\n%s' % top.head(5))
+    if entry_stream is not None:
+        th.cuda.set_stream(entry_stream)           # leave the caller's stream current again
     return best['auroc'], best['aupr']

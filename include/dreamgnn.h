@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 3
+#define DG_ABI_VERSION 4
 
 #define DG_OK 0
 #define DG_ERR_INVALID_ARGUMENT (-1)
@@ -232,6 +232,14 @@ DG_API size_t dg_knn_graph_workspace_bytes(int64_t n, int k);
 DG_API int dg_knn_graph_from_neighbors(const int32_t* nbr, int64_t n, int k, int32_t* indptr,
                                 int32_t* row, int32_t* col, float* val, int32_t* nnz_out,
                                 void* workspace, size_t workspace_bytes, dg_stream_t stream);
+
+/* ---- measurement support ------------------------------------------------------------------- */
+/* Read-bandwidth microbenchmark with the SpMM's access shape (scripts/l2_peak.py -> profiles/l2_peak.json): every warp
+ * of a 148 * ctas_per_sm CTA grid reads `rows_per_warp` rows of `row_floats` fp32 from buf [n_rows, row_floats] with
+ * 128-bit L1-bypassing loads, 4 rows in flight; rows are consecutive across warps (random = 0) or pseudo-random
+ * (random = 1). Bytes read = 148 * ctas_per_sm * 8 warps * rows_per_warp * row_floats * 4. Not on the product path. */
+DG_API int dg_bench_read_rows(const float* buf, int64_t n_rows, int64_t row_floats, int64_t rows_per_warp, int random,
+                       int ctas_per_sm, float* sink, dg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -19,31 +19,47 @@ import numpy as np
 
 REFERENCE_DIR = os.environ.get('DREAMGNN_REFERENCE_DIR', '/root/reference')
 ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+STAGED_ARCHIVE = os.path.join(ORACLE_DIR, '_ref', 'dreamgnn_reference.zip')     # oracle/stage_ref.py
 _REF_MODULES = ('utils', 'augmentation', 'data_loader', 'layers', 'model', 'evaluation', 'train')
 
 
+def reference_root():
+    """Where the unmodified reference modules import from: the source tree in the build container, else the archive
+    staged by oracle/stage_ref.py (what travels to the GPU box), else None."""
+    if os.path.isfile(os.path.join(REFERENCE_DIR, 'layers.py')):
+        return REFERENCE_DIR
+    if os.path.isfile(STAGED_ARCHIVE):
+        return STAGED_ARCHIVE
+    return None
+
+
 def reference_available():
-    return os.path.isfile(os.path.join(REFERENCE_DIR, 'layers.py'))
+    return reference_root() is not None
 
 
-def import_reference(quiet=True):
-    """Return a dict {name: module} of the reference's modules, imported unmodified."""
-    if not reference_available():
-        raise RuntimeError('reference sources not present at %s' % REFERENCE_DIR)
-    for p in (REFERENCE_DIR, ORACLE_DIR):
+def import_reference(quiet=True, replace=None):
+    """Return a dict {name: module} of the reference's modules, imported unmodified with `import dgl` resolving to the
+    stand-in in oracle/dgl. `replace` maps module names to already-imported modules that take their place BEFORE the
+    others are imported (the drop-in test puts this repo's `layers` and graph handle under the reference's own
+    `model.py` / `train.py` that way: {'dgl': ..., 'layers': ...})."""
+    root = reference_root()
+    if root is None:
+        raise RuntimeError('reference sources not present at %s and no staged archive at %s' % (REFERENCE_DIR, STAGED_ARCHIVE))
+    for p in (REFERENCE_DIR, STAGED_ARCHIVE, ORACLE_DIR):
         if p in sys.path:
             sys.path.remove(p)
-    sys.path.insert(0, REFERENCE_DIR)
+    sys.path.insert(0, root)
     sys.path.insert(0, ORACLE_DIR)        # `import dgl` -> oracle/dgl
+    replace = dict(replace or {})
+    for name in list(sys.modules):        # a different wiring than last time: re-import everything
+        if name in _REF_MODULES or name == 'dgl' or name.startswith('dgl.'):
+            del sys.modules[name]
+    sys.modules.update(replace)
     mods = {}
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink if quiet else sys.stdout):
         for name in _REF_MODULES:
-            m = sys.modules.get(name)
-            if m is None or not getattr(m, '__file__', '').startswith(REFERENCE_DIR):
-                sys.modules.pop(name, None)
-                m = importlib.import_module(name)
-            mods[name] = m
+            mods[name] = replace[name] if name in replace else importlib.import_module(name)
     return mods
 
 
