@@ -1,4 +1,4 @@
-"""`import dgl` for the reference, served by this package.
+"""The `dgl` module the reference imports, served by this package.
 
     import dreamgnn_b200.dgl_compat as dgl_compat
     dgl_compat.install()            # before the reference's modules are imported
@@ -22,7 +22,7 @@ def build_modules():
     from .layers import HeteroGraphConv
     dgl = types.ModuleType('dgl')
     dgl.__doc__ = 'DGL surface of DREAM-GNN served by dreamgnn_b200.graph (see dreamgnn_b200/dgl_compat.py)'
-    dgl.__path__ = []                                   # a package: `import dgl.function as fn` must resolve
+    dgl.__path__ = []                                   # a package: its `function` / `fn` / `nn.pytorch` submodules must resolve
     for name in ('heterograph', 'bipartite_from_scipy', 'DGLGraph', 'DGLHeteroGraph', 'DGLError', 'HeteroGraph'):
         setattr(dgl, name, getattr(_graph, name))
     fn = types.ModuleType('dgl.function')
