@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """Benchmark of DREAM-GNN's message-passing hot path on B200 (driver contract: one JSON line).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload syn20m|lrssl|gdataset|cdataset]
-    python bench.py --impl reference ...        # the reference's algorithm on the host CPU cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload syn20m|lrssl|gdataset|cdataset] [--aug default|full]
+    python bench.py --impl reference ...        # the reference's own training loop on the host CPU cores
 
 A "step" is one full training iteration (train.py:250-300): per-iteration augmentation (edge dropout
 + feature noise with the CSR rebuild), Net.forward, BCE + common loss, backward, clip, Adam.
 metric = aggregated edges per second: sum of nnz over every GCMC and FGCN SpMM launch (forward and
 backward) of one iteration / iteration time. iters/s is reported beside it.
 
-N > 1: one process per GPU (torchrun), each rank trains its own fold-replica of the same shape with
-no data-path collective (cross-validation folds shard embarrassingly) -> weak scaling; the timed
-region is bracketed by barrier + synchronize and the reported time is the max over ranks.
+N = 1 additionally reports, in the same line: `cpu_baseline` (the UNMODIFIED reference's train() loop on the host cores,
+on a bounded sample of the workload) with `same_shape` (this GPU arm timed on exactly that sample), and
+`extra_workloads` (BASELINE configs 1-3: lrssl / Gdataset / Cdataset at their full shapes in BOTH arms, plus lrssl with the
+full perturbation set and its rebuild time).
+N > 1: one process per GPU (torchrun), each rank trains its own fold-replica of the same shape with no data-path
+collective (cross-validation folds shard embarrassingly) -> weak scaling; the timed region is bracketed by barrier +
+synchronize and the reported time is the max over ranks. After it, `row_partitioned` times ONE graph 1-D
+row-partitioned over the N ranks (BASELINE config 5 path: NCCL all-gather / reduce-scatter per aggregation), with its
+NCCL share and a loss-parity check against the single-GPU path.
 """
 import argparse
+import gc
 import json
 import os
 import sys
+import tempfile
 import threading
 import time
 
@@ -27,6 +35,8 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 HBM_FALLBACK_GBS = 6650.0        # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+DENSE = ('lrssl', 'gdataset', 'cdataset')
+FULL_AUG = ['edge_dropout', 'add_random_edges', 'feature_noise', 'graph_noise', 'feature_masking', 'mix_up']
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -99,7 +109,7 @@ class ClockSampler:
                 'reasons': sorted(self.reasons), 'samples': len(sm)}
 
 
-def edge_sampler_label(args, state):
+def edge_sampler_label(cuda_graph, state):
     """Which sampler draws the edge dropout of the timed iterations (dreamgnn_b200.augmentation._randperm)."""
     from dreamgnn_b200.augmentation import SELECT_MIN_EDGES
     mode = os.environ.get('DG_EDGE_SAMPLER', 'auto')
@@ -108,101 +118,147 @@ def edge_sampler_label(args, state):
         big = any(g.number_of_edges(c) >= SELECT_MIN_EDGES for c in g.canonical_etypes)
     except AttributeError:                                   # row-partitioned state: per-rank blocks, eager launches
         big = False
-    if mode == 'select' or (mode == 'auto' and args.cuda_graph and big):
+    if mode == 'select' or (mode == 'auto' and cuda_graph and big):
         return 'uniform random k-subset by radix select (dg_random_subset_flags) for relations of >= %d edges' % SELECT_MIN_EDGES
     return 'th.randperm (reference-exact kept sets)'
 
 
-def spmm_algorithmic_bytes(nnz, n_rows, n_cols, d, elem, valued):
-    """SURVEY.md 8d gather model, the per-unit figure of the roofline: every stored edge reads its column
-    index (+ value) and one d-wide source row; every output row is written once; indptr and the two
-    scale vectors are read once."""
+def spmm_gather_bytes(nnz, n_rows, n_cols, d, elem, valued):
+    """SURVEY.md 8d gather model: every stored edge reads its column index (+ value) and one d-wide source row (from L2 or
+    HBM); every output row is written once; indptr and the two scale vectors are read once. = bytes moved L2 -> SM."""
     return nnz * (4 + (4 if valued else 0) + d * elem) + n_rows * d * 4 + (n_rows + 1) * 4 + (n_rows + n_cols) * 4
 
 
 def spmm_compulsory_bytes(nnz, n_rows, n_cols, d, elem, valued):
-    """B_min of SURVEY.md 8d: every operand touched exactly once (perfect reuse of gathered rows)."""
+    """B_min of SURVEY.md 8d: every operand touched exactly once (perfect reuse of gathered rows) = least HBM traffic."""
     return nnz * (4 + (4 if valued else 0)) + (n_rows + 1) * 4 + n_cols * d * elem + n_rows * d * 4 + (n_rows + n_cols) * 4
 
 
-# ---------------------------------------------------------------------------------------------------
-# B200 arm
-# ---------------------------------------------------------------------------------------------------
-def run_b200(args):
-    from dreamgnn_b200 import _lib, ops, synthetic
-    from dreamgnn_b200.model import Net
-    from dreamgnn_b200.train import train_iteration, aug_params_from_args
-    from dreamgnn_b200.utils import common_loss, common_loss_gram
+def _json_file(*parts):
+    p = os.path.join(REPO, *parts)
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return None
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not th.cuda.is_available():
-        raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
-    th.cuda.set_device(local)
-    dev = th.device('cuda', local)
-    _lib.load()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=dev)
-    if args.cuda_graph:
-        # nothing may ever touch the legacy default stream: autograd binds each parameter's gradient
-        # accumulation to the stream of its first use, and the legacy stream cannot take part in a capture
-        th.cuda.set_stream(th.cuda.Stream(device=dev))
-    if args.messages == 'bf16':
-        from dreamgnn_b200 import layers as _layers
-        _layers.MESSAGE_DTYPE = th.bfloat16
-    spec = synthetic.scaled(args.workload, args.scale)
-    rows = args.parallel == 'rows' and world > 1
-    seed = 1234 if rows else 1234 + rank                              # rows: one graph, identical on every rank
-    th.manual_seed(seed)
-    w = synthetic.make_workload(spec, dev, seed=seed)                  # folds: each rank its own fold-replica
+
+# ---------------------------------------------------------------------------------------------------
+# one measured workload on this rank's GPU
+# ---------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide setup shared by every measurement of a run."""
+
+    def __init__(self, args):
+        self.args = args
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not th.cuda.is_available():
+            raise RuntimeError('bench.py needs a CUDA device: the product path has no CPU fallback')
+        th.cuda.set_device(self.local)
+        self.dev = th.device('cuda', self.local)
+        from dreamgnn_b200 import _lib
+        _lib.load()
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group('nccl', device_id=self.dev)
+            self.dist = dist
+        # nothing may ever touch the legacy default stream: autograd binds each parameter's gradient accumulation to the
+        # stream of its first use, and the legacy stream cannot take part in a capture
+        th.cuda.set_stream(th.cuda.Stream(device=self.dev))
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        th.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = th.tensor([x], device=self.dev, dtype=th.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def build_state(ctx, workload, scale, seed):
+    """(spec, TrainState, Net args). Dense shapes go through the public loader on a `.mat` file (what a user runs);
+    the sparse synthetic shapes are generated on the device (the loader materialises dense N_d x N_s masks)."""
+    from dreamgnn_b200 import synthetic
+    spec = synthetic.scaled(workload, scale)
+    if spec['kind'] == 'dense' and scale == 1:
+        from dreamgnn_b200.data_loader import DrugDataLoader
+        from dreamgnn_b200.train import make_train_state
+        root = tempfile.mkdtemp(prefix='dg_bench_')
+        synthetic.write_mat(root, workload, seed=synthetic.MAT_SEEDS[workload] + 1000 * (seed - 1234))
+        old = os.getcwd()
+        os.chdir(root)
+        try:
+            ds = DrugDataLoader('lrssl', ctx.dev, symm=True, k=spec['k'], n_folds=10)
+        finally:
+            os.chdir(old)
+        state = make_train_state(ds, 0, ctx.dev)
+        w = dict(drug_feat=state.drug_feat, dis_feat=state.dis_feat, fdim_drug=spec['n_drug'], fdim_disease=spec['n_dis'])
+        return spec, state, synthetic.model_args(w), 'DrugDataLoader on a synthetic .mat of the reference schema, fold 0'
+    w = synthetic.make_workload(spec, ctx.dev, seed=seed)
+    state = synthetic.train_state(w, ctx.dev)
     margs = synthetic.model_args(w)
+    return spec, state, margs, 'generated on the device (dreamgnn_b200/synthetic.py)'
+
+
+def measure(ctx, workload, scale, steps, warmup, aug='default', cuda_graph=True, detail=False, e2e=True, seed=None):
+    """Time `steps` training iterations of `workload` on this rank's GPU. Returns a dict (ms are max over ranks)."""
+    from dreamgnn_b200 import _lib, ops
+    from dreamgnn_b200.model import Net
+    from dreamgnn_b200.train import aug_params_from_args, augment_state, train_iteration
+    from dreamgnn_b200.utils import common_loss, common_loss_gram
+    args, dev = ctx.args, ctx.dev
+    seed = (1234 + ctx.rank) if seed is None else seed                  # folds: each rank its own fold-replica
+    th.manual_seed(seed)
+    spec, state, margs, data_how = build_state(ctx, workload, scale, seed)
     model = Net(margs).to(dev)
-    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5, capturable=args.cuda_graph)
-    if rows:
-        from dreamgnn_b200 import dist as D
-        part = D.Partition({'drug': spec['n_drug'], 'disease': spec['n_dis']})
-        knn = {k: w[k] for k in ('drug_graph', 'disease_graph', 'drug_feature_graph', 'disease_feature_graph')}
-        state = D.PartitionedState(part, w['pairs'], w['labels'], knn, w['drug_feat'], w['dis_feat'],
-                                   w['drug_sim_feat'], w['dis_sim_feat'], dev)
-        state.labels = state.dec.labels
-        n_pairs_total = state.dec.n_global
-        th.manual_seed(4321 + rank)                                    # per-rank dropout / noise streams
-        step = lambda: D.train_iteration_partitioned(model, opt, state)
-    else:
-        state = synthetic.train_state(w, dev)
-        n_pairs_total = state.labels.numel()
-        loss_fn = th.nn.BCEWithLogitsLoss()
-        aug_methods = ['edge_dropout', 'feature_noise']
-        aug_params = aug_params_from_args(argparse.Namespace())
-        closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
-        step = lambda: train_iteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
-        eager_step, eager_launches = step, 0
-        if args.cuda_graph:
-            # kernels replayed from a graph are invisible to the C-ABI launch counter: count one eager step of the
-            # identical iteration (same kernels, same shapes) before capturing
-            from dreamgnn_b200.graphed import GraphedIteration
-            for _ in range(2):
-                step()
-            th.cuda.synchronize()
-            _lib.reset_launch_count()
-            step()
-            th.cuda.synchronize()
-            eager_launches = _lib.launch_count()
+    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5, capturable=cuda_graph)
+    loss_fn = th.nn.BCEWithLogitsLoss()
+    aug_methods = FULL_AUG if aug == 'full' else ['edge_dropout', 'feature_noise']
+    aug_params = aug_params_from_args(argparse.Namespace())
+    closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
+    step = lambda: train_iteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs)
+    eager_step, eager_launches = step, 0
+    n_pairs = int(state.labels.numel())
+    launch_mode = 'eager launches'
+    for _ in range(2):
+        step()
+    th.cuda.synchronize()
+    # the augmentation rebuild on its own (SURVEY 8d config 3: dropout compaction + CSR + CSC for the 4 etypes + the 4 kNN
+    # graphs, + the perturbation methods under --aug full): eager, CUDA events, average of 5
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        augment_state(state, aug_methods, aug_params)
+    e1.record()
+    th.cuda.synchronize()
+    aug_ms = e0.elapsed_time(e1) / 5
+    if cuda_graph:
+        # kernels replayed from a graph are invisible to the C-ABI launch counter: count one eager step of the identical
+        # iteration (same kernels, same shapes) before capturing
+        from dreamgnn_b200.graphed import GraphedIteration
+        _lib.reset_launch_count()
+        step()
+        th.cuda.synchronize()
+        eager_launches = _lib.launch_count()
+        try:
             step = GraphedIteration(model, opt, state, loss_fn, aug_methods, aug_params, 0.001, 1.0, closs,
                                     pipeline_aug=False if args.serial_aug else (True if args.pipeline_aug else None),
                                     parallel_routes=True if args.parallel_routes else (False if args.serial_aug else None))
-    del w
+            launch_mode = 'one CUDA-graph replay per step' + (
+                ' (augmentation of step i+1 on a parallel branch of step i)' if getattr(step, 'staged', None) is not None else '')
+        except Exception as e:                               # noqa: BLE001 -- an augmentation that cannot be captured
+            th.cuda.synchronize()
+            step, cuda_graph = eager_step, False
+            launch_mode = 'eager launches (capture failed: %s)' % str(e).splitlines()[0][:120]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        th.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
-    barrier()
+    ctx.barrier()
     # The caching allocator keeps growing its pool for a few more iterations (the kept-edge counts of the
     # augmentation differ from step to step); a cudaMalloc inside the timed region is a device-wide sync that
     # shows up as a 50-150 ms step. Keep warming up (untimed) until one whole step allocates nothing new.
@@ -214,253 +270,405 @@ def run_b200(args):
         extra_warmup += 1
         if th.cuda.memory_stats(dev).get('num_device_alloc', 0) == n0:
             break
-    barrier()
+    ctx.barrier()
 
-    # ---- timed region: exactly K steps, device-timed, SpMM launches logged with events -------------
-    import gc
+    # ---- timed region: exactly K steps, device-timed ----------------------------------------------
     gc.collect()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx.local)
     sampler.start()
     ops.PROFILE = []
     _lib.reset_launch_count()
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     stats0 = th.cuda.memory_stats(dev)
-    prof_range = os.environ.get('DG_PROFILE_RANGE') == '1'       # ncu --profile-from-start off
+    prof_range = detail and os.environ.get('DG_PROFILE_RANGE') == '1'       # ncu --profile-from-start off
     if prof_range:
         th.cuda.profiler.start()
     e0.record()
     marks, host_ms = [], []
-    for i in range(args.steps):
+    for i in range(steps):
         # bounded run-ahead: the host may be at most one full step ahead of the device. Letting it fill the
         # driver's launch queue made it block inside cudaLaunchKernel and (measured) stall the GPU for
         # 50-200 ms at random; an event wait on step i-2 costs nothing and keeps the queue from saturating.
         if i >= 2:
             marks[i - 2].synchronize()
         t_h = time.perf_counter()
-        loss = step()
+        step()
         host_ms.append(round((time.perf_counter() - t_h) * 1e3, 2))
         ev = th.cuda.Event(enable_timing=True)
         ev.record()
         marks.append(ev)
     e1.record()
-    barrier()
+    ctx.barrier()
+    if prof_range:
+        th.cuda.profiler.stop()
     step_ms = [round(a.elapsed_time(b), 2) for a, b in zip([e0] + marks[:-1], marks)]
     stats1 = th.cuda.memory_stats(dev)
     alloc_diag = {k: int(stats1.get(k, 0) - stats0.get(k, 0)) for k in ('num_device_alloc', 'num_device_free', 'num_alloc_retries')}
     alloc_diag['reserved_gb'] = round(stats1.get('reserved_bytes.all.current', 0) / 1e9, 1)
     alloc_diag['peak_allocated_gb'] = round(stats1.get('allocated_bytes.all.peak', 0) / 1e9, 1)
-    if prof_range:
-        th.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count()
     log, ops.PROFILE = ops.PROFILE, None
-    log_steps = args.steps
-    if args.cuda_graph and not rows:
+    log_steps = steps
+    if cuda_graph:
         # the graph replays carry no per-kernel events: the per-launch SpMM durations behind `roofline` come from
         # eager steps of the same iteration run right here (CUDA events around every SpMM launch on its stream),
         # while the clock sampler is still running
-        launches = getattr(step, 'launches_per_replay', eager_launches) * args.steps       # kernels recorded into the graph
-        log_steps = min(3, args.steps)
+        launches = getattr(step, 'launches_per_replay', eager_launches) * steps       # kernels recorded into the graph
+        log_steps = min(3, steps)
         ops.PROFILE = []
         for _ in range(log_steps):
             eager_step()
         th.cuda.synchronize()
         log, ops.PROFILE = ops.PROFILE, None
     clocks = sampler.stop()
-    t = th.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = ctx.max_over_ranks(ms)
+    res = {'workload': workload, 'scale': scale, 'spec': spec, 'n_pairs': n_pairs, 'ms_per_step': ms_max / steps,
+           'steps': steps, 'launches': int(launches), 'clocks': clocks, 'step_ms': step_ms, 'allocator': alloc_diag,
+           'host_enqueue_ms': host_ms, 'warmup_extra': extra_warmup, 'launch_mode': launch_mode, 'cuda_graph': cuda_graph,
+           'augmentation_rebuild_ms': round(aug_ms, 3), 'aug_methods': aug_methods, 'data_how': data_how,
+           'edge_sampler': edge_sampler_label(cuda_graph, state), 'log': log, 'log_steps': log_steps, 'timed_ms': ms,
+           'agg_edges': sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / max(log_steps, 1)}
 
     # ---- e2e: same K steps through the public API, host buffers in / loss out every step -----------
-    host = {k: getattr(state, k).cpu().pin_memory() for k in ('drug_feat', 'dis_feat', 'labels')}
-    sim_is_feat = state.drug_sim_feat is state.drug_feat
-    if not sim_is_feat:
-        host['drug_sim_feat'] = state.drug_sim_feat.cpu().pin_memory()
-        host['dis_sim_feat'] = state.dis_sim_feat.cpu().pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    # every step's inputs are copied from pinned host memory; the copy of step i+1 runs on a side stream
-    # while step i computes (double buffering), the step's loss is read back to the host every step
-    copy_stream = th.cuda.Stream(device=dev)
+    if e2e:
+        host = {k: getattr(state, k).cpu().pin_memory() for k in ('drug_feat', 'dis_feat', 'labels')}
+        sim_is_feat = state.drug_sim_feat is state.drug_feat
+        if not sim_is_feat:
+            host['drug_sim_feat'] = state.drug_sim_feat.cpu().pin_memory()
+            host['dis_sim_feat'] = state.dis_sim_feat.cpu().pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        # every step's inputs are copied from pinned host memory; the copy of step i+1 runs on a side stream
+        # while step i computes (double buffering), the step's loss is read back to the host every step
+        copy_stream = th.cuda.Stream(device=dev)
 
-    def upload():
-        with th.cuda.stream(copy_stream):
-            bufs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            ev = th.cuda.Event()
-            ev.record(copy_stream)
-        return bufs, ev
+        def upload():
+            with th.cuda.stream(copy_stream):
+                bufs = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                ev = th.cuda.Event()
+                ev.record(copy_stream)
+            return bufs, ev
 
-    def e2e_steps(n):
-        nxt = upload()
-        last = None
-        for i in range(n):
-            bufs, ev = nxt
-            th.cuda.current_stream().wait_event(ev)
-            for k, v in bufs.items():
-                v.record_stream(th.cuda.current_stream())
-                if args.cuda_graph and not rows:
-                    getattr(state, k).copy_(v)        # the captured graph reads its own static input buffers
-                else:
-                    setattr(state, k, v)
-            if sim_is_feat and not (args.cuda_graph and not rows):
-                state.drug_sim_feat, state.dis_sim_feat = state.drug_feat, state.dis_feat
-            if rows:
-                state.dec.labels = state.labels
-            if i + 1 < n:
-                nxt = upload()                                            # prefetch the next step's inputs
-            last = float(step().item())                                   # D2H read of the step's result
-        return last
+        def e2e_steps(n):
+            nxt = upload()
+            last = None
+            for i in range(n):
+                bufs, ev = nxt
+                th.cuda.current_stream().wait_event(ev)
+                for k, v in bufs.items():
+                    v.record_stream(th.cuda.current_stream())
+                    if cuda_graph:
+                        getattr(state, k).copy_(v)        # the captured graph reads its own static input buffers
+                    else:
+                        setattr(state, k, v)
+                if sim_is_feat and not cuda_graph:
+                    state.drug_sim_feat, state.dis_sim_feat = state.drug_feat, state.dis_feat
+                if i + 1 < n:
+                    nxt = upload()                                            # prefetch the next step's inputs
+                last = float(step().item())                                   # D2H read of the step's result
+            return last
 
-    e2e_steps(3)            # untimed: the upload buffers enter the allocator's pool (a cudaMalloc mid-loop stalls the device)
-    barrier()
-    e0.record()
-    loss_host = e2e_steps(args.steps)
-    e1.record()
-    barrier()
-    t = th.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+        e2e_steps(3)        # untimed: the upload buffers enter the allocator's pool (a cudaMalloc mid-loop stalls the device)
+        ctx.barrier()
+        e0.record()
+        loss_host = e2e_steps(steps)
+        e1.record()
+        ctx.barrier()
+        res.update(e2e_ms_per_step=ctx.max_over_ranks(e0.elapsed_time(e1)) / steps, h2d_bytes=int(h2d), final_loss=loss_host,
+                   e2e_what='features + labels copied from pinned host memory every step (next step prefetched on a side '
+                            'stream while the current one computes%s), loss read back every step; graph structure stays '
+                            'resident as in the reference training loop (train.py:186-200)'
+                            % (', then copied device-to-device into the captured graph\'s input buffers' if cuda_graph else ''))
+    del step, eager_step, model, opt, state
+    gc.collect()
+    th.cuda.empty_cache()
+    return res
 
-    # ---- metric ---------------------------------------------------------------------------------
-    agg_edges = sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / log_steps
-    it_s = args.steps / (ms_max / 1e3)
-    if rows:                                                          # one job: edges are summed over ranks
-        t = th.tensor([agg_edges], device=dev, dtype=th.float64)
-        dist.all_reduce(t)
-        agg_edges = float(t.item())
-        value, e2e_value = agg_edges * it_s / 1e9, agg_edges * (args.steps / (ms_e2e / 1e3)) / 1e9
-    else:                                                             # N independent fold-replicas
-        value = world * agg_edges * it_s / 1e9
-        e2e_value = world * agg_edges * (args.steps / (ms_e2e / 1e3)) / 1e9
 
-    # ---- roofline of the dominant kernel (largest total device time among the logged SpMM classes) --
+def roofline_block(res):
+    """Roofline of the dominant SpMM class (largest device time among the logged classes) from the per-launch events."""
+    from dreamgnn_b200 import build as _build
+    log, log_steps = res['log'], res['log_steps']
     classes = {}
     for tag, nnz, nr, nc, d, el, valued, a, b in log:
         key = (tag.split('.')[0], d, el)
-        c = classes.setdefault(key, dict(ms=0.0, bytes=0.0, bmin=0.0, n=0, nnz=0))
+        c = classes.setdefault(key, dict(ms=0.0, gather=0.0, bmin=0.0, n=0, nnz=0))
         c['ms'] += a.elapsed_time(b)
-        c['bytes'] += spmm_algorithmic_bytes(nnz, nr, nc, d, el, valued)
+        c['gather'] += spmm_gather_bytes(nnz, nr, nc, d, el, valued)
         c['bmin'] += spmm_compulsory_bytes(nnz, nr, nc, d, el, valued)
         c['n'] += 1
         c['nnz'] += nnz
     per_step = len(log) // max(log_steps, 1)
-    spmm_ms_by_step = [round(sum(r[7].elapsed_time(r[8]) for r in log[i * per_step:(i + 1) * per_step]), 2)
-                       for i in range(log_steps)] if per_step else []
-    # per-launch view (same events): launch i of a step averaged over the logged steps
     per_launch = []
-    for i in range(per_step):
+    for i in range(per_step):                                 # launch i of a step averaged over the logged steps
         recs = [log[s_ * per_step + i] for s_ in range(log_steps)]
         tag, nnz, nr, nc, d, el, valued = recs[0][:7]
         t_ms = sum(r[7].elapsed_time(r[8]) for r in recs) / log_steps
         per_launch.append({'tag': tag, 'rows': int(nr), 'cols': int(nc), 'nnz': int(nnz), 'd': int(d),
                            'operand_mb': round(nc * d * el / 1e6, 1), 'ms': round(t_ms, 3),
-                           'gather_GBps': round(spmm_algorithmic_bytes(nnz, nr, nc, d, el, valued) / (t_ms / 1e3) / 1e9, 1)})
+                           'gather_GBps': round(spmm_gather_bytes(nnz, nr, nc, d, el, valued) / (t_ms / 1e3) / 1e9, 1)})
     top_key, top = max(classes.items(), key=lambda kv: kv[1]['ms'])
     peak, peak_src = measured_peak()
-    achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
-    traffic = None
-    tp = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
-    if os.path.isfile(tp):
-        with open(tp) as fh:
-            traffic = json.load(fh).get('%s_d%d' % (top_key[0], top_key[1]))
-    roofline = {'bound': 'hbm', 'kernel': 'spmm_csr_kernel (%s, d=%d, %d-byte features)' % top_key,
-                'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
-                'traffic': traffic,
-                # the three readings of "fraction of HBM peak": gather-model (`frac`, L2-served re-reads counted), actual
-                # DRAM traffic per launch from the committed ncu capture, and the no-reuse lower bound (`compulsory_frac`)
-                'dram_GBps': round(traffic / (top['ms'] / top['n'] / 1e3) / 1e9, 1) if traffic else None,
-                'dram_frac': round(traffic / (top['ms'] / top['n'] / 1e3) / 1e9 / peak, 4) if traffic else None,
-                'peak_source': peak_src, 'launches_timed': top['n'],
-                'avg_launch_ms': round(top['ms'] / top['n'], 4),
-                'algorithmic_bytes_per_launch': int(top['bytes'] / top['n']),
-                'model': 'gather: nnz*(4[+4]+d*s) + n_rows*d*4 + index/scale vectors (SURVEY 8d)',
-                'compulsory_frac': round(top['bmin'] / (top['ms'] / 1e3) / 1e9 / peak, 4),
-                'share_of_step': round(top['ms'] / log_steps / (ms / args.steps), 4),
-                'timed_in': ('%d eager steps of the same iteration run after the graph-replayed timed region' % log_steps)
-                            if (args.cuda_graph and not rows) else 'the timed region',
-                'all_spmm_classes': {'%s_d%d_b%d' % k: {'ms_per_step': round(v['ms'] / log_steps, 3),
-                                                        'GBps': round(v['bytes'] / (v['ms'] / 1e3) / 1e9, 1),
-                                                        'GEps': round(v['nnz'] / (v['ms'] / 1e3) / 1e9, 2)}
-                                     for k, v in classes.items()}}
+    avg_s = top['ms'] / top['n'] / 1e3
+    # DRAM traffic per launch: ncu dram__bytes of THIS kernel build (profiles/roofline_traffic.json carries the digest of
+    # the SpMM sources it was captured from; a stale capture is not used)
+    traffic, traffic_src = None, 'no ncu capture on file'
+    tr = _json_file('profiles', 'roofline_traffic.json')
+    if tr is not None:
+        digest = _build.kernel_digest(['spmm.cu', 'common.cuh'])
+        if tr.get('kernel_digest') == digest:
+            traffic = tr.get('%s_d%d' % (top_key[0], top_key[1]))
+            traffic_src = tr.get('source', 'profiles/roofline_traffic.json')
+        else:
+            traffic_src = 'profiles/roofline_traffic.json was captured from another build of spmm.cu (digest %s != %s): ignored' % (
+                tr.get('kernel_digest'), digest)
+    l2 = _json_file('profiles', 'l2_peak.json') or {}
+    l2_key = 'l2_gather_d%d' % top_key[1]
+    l2_peak = (l2.get(l2_key) or l2.get('l2_seq') or {}).get('GBps')
+    gather_gbps = top['gather'] / (top['ms'] / 1e3) / 1e9
+    bmin_gbps = top['bmin'] / (top['ms'] / 1e3) / 1e9
+    if traffic is not None:
+        achieved, basis = traffic / avg_s / 1e9, 'DRAM traffic of the launch (ncu dram__bytes_read + dram__bytes_write) / CUDA-event duration'
+    else:
+        achieved, basis = bmin_gbps, 'compulsory bytes B_min (SURVEY 8d; every operand once) / CUDA-event duration'
+    return {'bound': 'hbm', 'kernel': 'spmm_csr_kernel (%s, d=%d, %d-byte features)' % top_key,
+            'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
+            'traffic': traffic, 'basis': basis, 'traffic_source': traffic_src, 'peak_source': peak_src,
+            'launches_timed': top['n'], 'avg_launch_ms': round(avg_s * 1e3, 4),
+            'compulsory_bytes_per_launch': int(top['bmin'] / top['n']), 'compulsory_GBps': round(bmin_gbps, 1),
+            'compulsory_frac': round(bmin_gbps / peak, 4),
+            # the gather model counts every stored edge's source row: bytes moved L2 -> SM, quoted against the measured L2
+            # gather ceiling of the same access shape (profiles/l2_peak.json, scripts/l2_peak.py), not against HBM
+            'l2_gather_bytes_per_launch': int(top['gather'] / top['n']), 'l2_gather_GBps': round(gather_gbps, 1),
+            'l2_peak_GBps': l2_peak, 'l2_peak_source': ('profiles/l2_peak.json:' + l2_key) if l2_peak else None,
+            'l2_frac': round(gather_gbps / l2_peak, 4) if l2_peak else None,
+            'share_of_step': round(top['ms'] / log_steps / res['ms_per_step'], 4),
+            'timed_in': ('%d eager steps of the same iteration run after the graph-replayed timed region' % log_steps)
+                        if res['cuda_graph'] else 'the timed region',
+            'all_spmm_classes': {'%s_d%d_b%d' % k: {'ms_per_step': round(v['ms'] / log_steps, 3),
+                                                    'l2_gather_GBps': round(v['gather'] / (v['ms'] / 1e3) / 1e9, 1),
+                                                    'compulsory_GBps': round(v['bmin'] / (v['ms'] / 1e3) / 1e9, 1),
+                                                    'GEps': round(v['nnz'] / (v['ms'] / 1e3) / 1e9, 2)}
+                                 for k, v in classes.items()}}, per_launch
 
+
+# ---------------------------------------------------------------------------------------------------
+# row-partitioned path (N > 1): one graph, 1-D row partition, NCCL all-gather / reduce-scatter per aggregation
+# ---------------------------------------------------------------------------------------------------
+def measure_rows(ctx, workload, scale, steps, warmup, single_gpu_ms=None):
+    from dreamgnn_b200 import dist as D, ops, synthetic
+    from dreamgnn_b200.model import Net
+    from dreamgnn_b200.utils import common_loss_gram
+    dev, dist = ctx.dev, ctx.dist
+    spec = synthetic.scaled(workload, scale)
+    for k in ('n_drug', 'n_dis'):
+        spec[k] -= spec[k] % ctx.world
+    th.manual_seed(1234)
+    w = synthetic.make_workload(spec, dev, seed=1234)                  # one graph, identical on every rank
+    model = Net(synthetic.model_args(w)).to(dev)
+    part = D.Partition({'drug': spec['n_drug'], 'disease': spec['n_dis']})
+    knn = {k: w[k] for k in ('drug_graph', 'disease_graph', 'drug_feature_graph', 'disease_feature_graph')}
+    state = D.PartitionedState(part, w['pairs'], w['labels'], knn, w['drug_feat'], w['dis_feat'], w['drug_sim_feat'],
+                               w['dis_sim_feat'], dev)
+    # ---- loss parity: the partitioned forward (no augmentation, eval-mode dropout) against the single-GPU path ----
+    model.eval()
+    with th.no_grad():
+        feats = (state.drug_feat, state.dis_feat, state.drug_sim_feat, state.dis_sim_feat)
+        local, bce, common = D.partitioned_loss(model, state, state.enc_graph, state.knn, feats)
+        loss_rows = float(D.all_reduce_sum(bce) + 0.001 * common)
+        full = synthetic.train_state(w, dev)
+        pred, a, b, c, d_ = model(full.enc_graph, full.dec_graph, full.drug_graph, full.drug_sim_feat, full.drug_feat,
+                                  full.dis_graph, full.dis_sim_feat, full.dis_feat, full.drug_feature_graph,
+                                  full.disease_feature_graph)
+        loss_one = float(th.nn.functional.binary_cross_entropy_with_logits(pred.squeeze(-1), full.labels)
+                         + 0.001 * (common_loss_gram(a, b) + common_loss_gram(c, d_)))
+        del full, pred, a, b, c, d_
+    n_pairs = int(w['labels'].numel())
+    del w, knn
+    gc.collect()
+    th.cuda.empty_cache()
+    model.train()
+    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5)
+    th.manual_seed(4321 + ctx.rank)                                    # per-rank dropout / noise streams
+    step = lambda: D.train_iteration_partitioned(model, opt, state)
+    for _ in range(max(warmup, 3) + 2):
+        step()
+    ctx.barrier()
+    ops.PROFILE, D.PROFILE = [], []
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    log, ops.PROFILE = ops.PROFILE, None
+    clog, D.PROFILE = D.PROFILE, None
+    edges = th.tensor([sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / steps], device=dev, dtype=th.float64)
+    dist.all_reduce(edges)
+    nccl_ms = ctx.max_over_ranks(sum(a.elapsed_time(b) for _, _, a, b in clog if a is not None) / steps)
+    nccl_bytes = sum(nb for _, nb, _, _ in clog) / steps
+    by_kind = {}
+    for kind, nb, a, b in clog:                               # deferred all-gathers log their bytes here and their exposed
+        k = by_kind.setdefault(kind, {'calls_per_step': 0, 'bytes_per_step': 0, 'ms_per_step': 0.0})    # time under *_wait
+        k['calls_per_step'] += 1.0 / steps
+        k['bytes_per_step'] += nb / steps
+        k['ms_per_step'] += (a.elapsed_time(b) if a is not None else 0.0) / steps
+    for k in by_kind.values():
+        k['calls_per_step'], k['bytes_per_step'], k['ms_per_step'] = round(k['calls_per_step'], 1), int(k['bytes_per_step']), round(k['ms_per_step'], 3)
+    rel = abs(loss_rows - loss_one) / max(abs(loss_one), 1e-30)
+    out = {'workload': '%s: %d drugs x %d diseases, %d scored pairs, ONE graph 1-D row-partitioned over %d GPUs'
+                       % (workload, spec['n_drug'], spec['n_dis'], n_pairs, ctx.world),
+           'ms_per_step': round(ms, 3), 'iters_per_sec': round(1e3 / ms, 4), 'GE/s': round(float(edges.item()) / (ms / 1e3) / 1e9, 4),
+           'scaling': 'strong', 'steps': steps,
+           'strong_scaling_vs_1gpu': round(single_gpu_ms / ms, 3) if single_gpu_ms else None,
+           'single_gpu_ms_per_step': round(single_gpu_ms, 3) if single_gpu_ms else None,
+           'nccl_bytes_per_step': int(nccl_bytes), 'nccl_ms_per_step': round(nccl_ms, 3), 'nccl_share_of_step': round(nccl_ms / ms, 4),
+           'collectives': by_kind,
+           'nccl_timing': 'CUDA events on the compute stream around every blocking collective and around the stream-wait of '
+                          'every deferred all-gather (rank-local sum, max over ranks) = the time the compute stream is held '
+                          'by communication',
+           'loss_matches_1gpu': {'loss_rows': loss_rows, 'loss_1gpu': loss_one, 'rel_diff': rel, 'ok': bool(rel <= 1e-5),
+                                 'what': 'eval-mode forward + BCE + beta*common of the same weights on the same graph: N-rank '
+                                         'partitioned path vs the single-GPU path on rank 0..N-1 (every rank holds the full graph once)'},
+           'launch': 'eager launches (NCCL inside the step)'}
+    del state, model, opt
+    gc.collect()
+    th.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    ctx = Ctx(args)
+    world, rank = ctx.world, ctx.rank
+    if args.messages == 'bf16':
+        from dreamgnn_b200 import layers as _layers
+        _layers.MESSAGE_DTYPE = th.bfloat16
+    if args.parallel == 'rows' and world > 1:                        # explicit row-partitioned run: that IS the line
+        r = measure_rows(ctx, args.workload, args.scale, args.steps, args.warmup)
+        if rank == 0:
+            emit({'metric': 'aggregated_edges_per_sec', 'value': r['GE/s'], 'unit': 'GE/s', 'n_gpus': world, 'steps': args.steps,
+                  'warmup': max(args.warmup, 3), 'ms_per_step': r['ms_per_step'], 'iters_per_sec': r['iters_per_sec'],
+                  'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                  'config': {'workload': r['workload'], 'parallelism': '1-D row partition, NCCL all-gather of node rows per aggregation'},
+                  'row_partitioned': r, 'gpu_launches': None})
+        ctx.dist.destroy_process_group()
+        return
+
+    res = measure(ctx, args.workload, args.scale, args.steps, args.warmup, aug=args.aug, cuda_graph=args.cuda_graph, detail=True)
+    spec = res['spec']
+    roofline, per_launch = roofline_block(res)
+    it_s = 1e3 / res['ms_per_step']
+    value = world * res['agg_edges'] * it_s / 1e9                    # N independent fold-replicas
+    e2e_value = world * res['agg_edges'] * (1e3 / res['e2e_ms_per_step']) / 1e9
+    top_bmin = roofline['compulsory_bytes_per_launch']
     out = {'metric': 'aggregated_edges_per_sec', 'value': round(value, 4), 'unit': 'GE/s', 'n_gpus': world,
-           'steps': args.steps, 'warmup': max(args.warmup, 3), 'warmup_extra': extra_warmup,
-           'ms_per_step': round(ms_max / args.steps, 3),
-           'iters_per_sec': round((1 if rows else world) * it_s, 4), 'higher_is_better': True,
-           'scaling': 'strong' if rows else 'weak',
-           'vs_baseline': None, 'dtype': 'f32' if args.messages == 'f32' else 'bf16 messages / f32 accumulate',
-           'data': 'synthetic',
+           'steps': args.steps, 'warmup': max(args.warmup, 3), 'warmup_extra': res['warmup_extra'],
+           'ms_per_step': round(res['ms_per_step'], 3), 'iters_per_sec': round(world * it_s, 4), 'higher_is_better': True,
+           'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'f32' if args.messages == 'f32' else 'bf16 messages / f32 accumulate', 'data': 'synthetic',
            'config': {'workload': '%s: %d drugs x %d diseases, %d scored pairs, %d-/%d-dim features, k=%d, '
                                   'GCMC+FGCN 3 layers, 128 units, one fold per GPU'
-                                  % (args.workload, spec['n_drug'], spec['n_dis'], n_pairs_total,
-                                     spec['f_drug'], spec['f_dis'], spec['k']),
-                      'step': 'augmentation + forward + loss + backward + clip + Adam (train.py:250-300)',
-                      'aggregated_edges_per_step': int(agg_edges), 'scale': args.scale,
-                      'launch': ('one CUDA-graph replay per step' + (' (augmentation of step i+1 on a parallel branch of step i)'
-                                                                   if getattr(step, 'staged', None) is not None else ''))
-                                if args.cuda_graph else 'eager launches',
-                      'l2': 'inputs larger than L2 (gathered operand %.0f MB, indices %.0f MB per SpMM)'
-                            % (top['bmin'] / top['n'] / 1e6, top['nnz'] / top['n'] * 4 / 1e6)
-                            if top['bmin'] / top['n'] > 126e6 else 'working set fits L2; no flush between steps',
-                      'edge_sampler': edge_sampler_label(args, state),
-                      'parallelism': ('1-D row partition, NCCL all-gather of node rows per aggregation' if rows else
-                                      'fold-replica per GPU, no collective') if world > 1 else 'single GPU',
+                                  % (args.workload, spec['n_drug'], spec['n_dis'], res['n_pairs'], spec['f_drug'], spec['f_dis'], spec['k']),
+                      'step': 'augmentation (%s) + forward + loss + backward + clip + Adam (train.py:250-300)' % ' '.join(res['aug_methods']),
+                      'aggregated_edges_per_step': int(res['agg_edges']), 'scale': args.scale, 'launch': res['launch_mode'],
+                      'inputs': res['data_how'],
+                      'l2': 'inputs larger than L2 (gathered operand %.0f MB per SpMM launch of the dominant class)' % (top_bmin / 1e6)
+                            if top_bmin > 126e6 else 'working set fits L2; no flush between steps',
+                      'edge_sampler': res['edge_sampler'],
+                      'parallelism': 'fold-replica per GPU, no collective' if world > 1 else 'single GPU',
                       'common_loss': 'N x N (reference form)' if spec['kind'] == 'dense' else
                                      'Gram-matrix form of the same value (N x N does not fit at this shape)',
                       'fgcn_input': 'N x N similarity (reference)' if spec['kind'] == 'dense' else
                                     'feature matrix (N x N similarity infeasible at this shape)'},
-           'e2e': {'value': round(e2e_value, 4), 'unit': 'GE/s', 'ms_per_step': round(ms_e2e / args.steps, 3),
-                   'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 4,
-                   'what': 'features + labels copied from pinned host memory every step (next step prefetched on a side '
-                           'stream while the current one computes%s), loss read back every step; graph structure stays '
-                           'resident as in the reference training loop (train.py:186-200)'
-                           % ((', then copied device-to-device into the captured graph\'s input buffers'
-                               + ('; the augmentation branch of replay i draws from them for replay i+1'
-                                  if getattr(step, 'staged', None) is not None else ''))
-                              if (args.cuda_graph and not rows) else '')},
-           'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'step_ms': step_ms, 'allocator': alloc_diag, 'host_enqueue_ms': host_ms, 'spmm_ms_by_step': spmm_ms_by_step, 'spmm_launches': per_launch,
-           'final_loss': round(loss_host, 6)}
+           'e2e': {'value': round(e2e_value, 4), 'unit': 'GE/s', 'ms_per_step': round(res['e2e_ms_per_step'], 3),
+                   'h2d_bytes_per_step': res['h2d_bytes'], 'd2h_bytes_per_step': 4, 'what': res['e2e_what']},
+           'gpu_launches': res['launches'], 'clocks': res['clocks'], 'roofline': roofline,
+           'augmentation_rebuild_ms': res['augmentation_rebuild_ms'], 'step_ms': res['step_ms'], 'allocator': res['allocator'],
+           'host_enqueue_ms': res['host_enqueue_ms'], 'spmm_launches': per_launch, 'final_loss': round(res['final_loss'], 6)}
+    single_ms = res['ms_per_step']
+    del res
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_reference(args, steps=1, warmup=1)
+    if world == 1 and not args.no_cpu_baseline:
+        base = cpu_reference(args.workload, args.scale, steps=1, warmup=1, cpu_scale=args.cpu_scale)
+        # the GPU arm on EXACTLY the sample the CPU arm ran: the same-workload ratio
+        if 'sample_scale' in base:
+            g = measure(ctx, args.workload, base['sample_scale'], steps=20, warmup=3, cuda_graph=args.cuda_graph, e2e=True, seed=1234)
+            base['same_shape'] = {'workload': '%s at scale %.5g: %d drugs x %d diseases, %d scored pairs'
+                                              % (args.workload, base['sample_scale'], g['spec']['n_drug'], g['spec']['n_dis'], g['n_pairs']),
+                                  'gpu_ms_per_step': round(g['ms_per_step'], 3), 'gpu_e2e_ms_per_step': round(g['e2e_ms_per_step'], 3),
+                                  'cpu_ms_per_step': base['ms_per_step'], 'ratio': round(base['ms_per_step'] / g['ms_per_step'], 1),
+                                  'e2e_ratio': round(base['ms_per_step'] / g['e2e_ms_per_step'], 1), 'same_config': True}
+        out['cpu_baseline'] = base
+        if args.workload == 'syn20m' and args.scale == 1.0 and not args.no_extra:
+            out['extra_workloads'] = extra_workloads(ctx, args)
+    if world > 1 and not args.no_rows:
+        try:
+            out['row_partitioned'] = measure_rows(ctx, args.workload, args.scale, max(3, min(args.steps, 10)), 3,
+                                                  single_gpu_ms=single_ms)
+        except Exception as e:                                   # noqa: BLE001 -- never lose the main line
+            out['row_partitioned'] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:300])}
     if rank == 0:
         emit(out)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
+
+
+def extra_workloads(ctx, args):
+    """BASELINE configs 1-3 at their FULL shapes in both arms: the B200 path (graph replay, device-timed and end to end) and
+    the unmodified reference's train() loop on the host cores, on the same `.mat` dataset; lrssl also with the full
+    perturbation set (config 3) and the rebuild time on its own."""
+    from dreamgnn_b200 import synthetic
+    out = {}
+    for name in DENSE:
+        try:
+            g = measure(ctx, name, 1.0, steps=50, warmup=5, cuda_graph=True, e2e=True, seed=1234)
+            e = {'config': '%s shape: %d drugs x %d diseases, %d training pairs, 768-dim embeddings, k=%d, one fold'
+                           % (name, g['spec']['n_drug'], g['spec']['n_dis'], g['n_pairs'], g['spec']['k']),
+                 'gpu_ms_per_iter': round(g['ms_per_step'], 4), 'gpu_iters_per_sec': round(1e3 / g['ms_per_step'], 1),
+                 'gpu_e2e_ms_per_iter': round(g['e2e_ms_per_step'], 4), 'h2d_bytes_per_step': g['h2d_bytes'],
+                 'GE/s': round(g['agg_edges'] / (g['ms_per_step'] / 1e3) / 1e9, 4), 'gpu_launches_per_iter': g['launches'] // g['steps'],
+                 'augmentation_rebuild_ms': g['augmentation_rebuild_ms'], 'launch': g['launch_mode']}
+            cpu = cpu_reference(name, 1.0, steps=2, warmup=1, mat_seed=synthetic.MAT_SEEDS[name])
+            e.update(cpu_ms_per_iter=cpu['ms_per_step'], cpu_kind=cpu['kind'], cpu_cores=cpu['cores'],
+                     ratio=round(cpu['ms_per_step'] / g['ms_per_step'], 1), e2e_ratio=round(cpu['ms_per_step'] / g['e2e_ms_per_step'], 1),
+                     same_config=True)
+            if name == 'lrssl':
+                f = measure(ctx, name, 1.0, steps=20, warmup=3, aug='full', cuda_graph=True, e2e=False, seed=1234)
+                e['aug_full'] = {'methods': f['aug_methods'], 'gpu_ms_per_iter': round(f['ms_per_step'], 4),
+                                 'augmentation_rebuild_ms': f['augmentation_rebuild_ms'], 'launch': f['launch_mode']}
+            out[name] = e
+        except Exception as ex:                                  # noqa: BLE001 -- never lose the main line
+            out[name] = {'error': '%s: %s' % (type(ex).__name__, str(ex).splitlines()[0][:300])}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle/restate.py port -- the reference is pure Python + DGL and
-# cannot travel to the GPU box) on all host cores, on a bounded proportional sample of the workload
+# CPU arm: the UNMODIFIED reference's own train() loop (oracle/ref_bench.py; reference modules from /root/reference or the
+# archive staged in oracle/_ref, `import dgl` -> the pure-torch stand-in) on all host cores, on a bounded sample of the
+# workload. Falls back to the oracle port (oracle/restate.py) only when no reference is available on this machine.
 # ---------------------------------------------------------------------------------------------------
 def cpu_sample_workload(workload, scale, seed=1234):
-    """Same generator as the GPU arm, on CPU with numpy/torch: a proportional replica (nodes and pairs
-    scaled together, widths and k unchanged) so the per-edge work matches the full shape."""
+    """The sparse generator of the GPU arm, on CPU: a proportional replica (nodes and pairs scaled together, widths and k
+    unchanged) so the per-edge work matches the full shape."""
     import numpy as np
     from dreamgnn_b200 import synthetic
     from oracle import restate as R
     spec = synthetic.scaled(workload, scale)
     gen = th.Generator().manual_seed(seed)
     n_d, n_s = spec['n_drug'], spec['n_dis']
-    if spec['kind'] == 'sparse':
-        cells = th.unique(th.randint(0, n_d * n_s, (spec['n_pairs'],), generator=gen))
-        labels = (th.rand(cells.numel(), generator=gen) < 0.01).float()
-        fdim = (spec['f_drug'], spec['f_dis'])
-    else:
-        perm = th.randperm(n_d * n_s, generator=gen)
-        pos, neg = perm[:spec['n_pos']], perm[spec['n_pos']:]
-        pos, neg = pos[:int(pos.numel() * 0.9)], neg[:int(neg.numel() * 0.9)]
-        cells = th.cat([th.sort(pos).values, th.sort(neg).values])
-        labels = th.cat([th.ones(pos.numel()), th.zeros(neg.numel())])
-        fdim = (n_d, n_s)
+    cells = th.unique(th.randint(0, n_d * n_s, (spec['n_pairs'],), generator=gen))
+    labels = (th.rand(cells.numel(), generator=gen) < 0.01).float()
     order = th.argsort(labels, descending=True, stable=True)
     cells, labels = cells[order], labels[order]
     pairs = ((cells // n_s).numpy(), (cells % n_s).numpy())
     drug_feat = th.nn.functional.normalize(th.randn(n_d, spec['f_drug'], generator=gen), dim=1)
     dis_feat = th.nn.functional.normalize(th.randn(n_s, spec['f_dis'], generator=gen), dim=1)
-    enc = R.enc_graph_from_pairs(pairs, labels.numpy(), n_d, n_s)
 
     def knn(x):
         x = np.asarray(x, dtype=np.float64)
@@ -469,39 +677,78 @@ def cpu_sample_workload(workload, scale, seed=1234):
     emb_d = th.randn(n_d, 64, generator=gen).numpy()
     emb_s = th.randn(n_s, 64, generator=gen).numpy()
     graphs = [knn(emb_d), knn(emb_s), knn(drug_feat.numpy()), knn(dis_feat.numpy())]
-    if spec['kind'] == 'sparse':
-        sims = (drug_feat, dis_feat)
+    return spec, pairs, labels, graphs, (drug_feat, dis_feat)
+
+
+def _cpu_model():
+    try:
+        with open('/proc/cpuinfo') as fh:
+            return next((ln.split(':', 1)[1].strip() for ln in fh if ln.startswith('model name')), '')
+    except OSError:
+        return ''
+
+
+def cpu_reference(workload, scale, steps, warmup, budget_s=25.0, cpu_scale=0.0, mat_seed=None):
+    """Time `steps` training iterations of the reference on all host cores. Dense shapes run at the given scale (full
+    shape: ~2 s / iteration); sparse shapes on a proportional sample sized from a small probe so that (warmup + steps)
+    fit `budget_s` (capped at scale / 40), unless `cpu_scale` names the sample."""
+    from dreamgnn_b200 import synthetic
+    from oracle import ref_bench as RB, ref_runner as rr
+    cores = os.cpu_count() or 1
+    th.set_num_threads(cores)
+    if not RB.available():
+        return cpu_port(workload, scale, steps, warmup, budget_s, cpu_scale)
+    mods = rr.import_reference()
+    sparse = synthetic.SHAPES[workload]['kind'] == 'sparse'
+    if sparse:
+        s = cpu_scale
+        if not s:
+            cap = scale / 40.0
+            probe_scale = min(cap, 0.004)
+            spec, pairs, labels, graphs, feats = cpu_sample_workload(workload, probe_scale)
+            ds = RB.sparse_dataset(mods, pairs, labels.numpy(), spec['n_drug'], spec['n_dis'], feats[0], feats[1], graphs)
+            per_pair = RB.time_train(mods, ds, steps=1, warmup=0)[0] / len(labels)
+            full_pairs = len(labels) / probe_scale
+            s = max(min(cap, budget_s / max(steps + warmup, 1) / per_pair / full_pairs), probe_scale)
+        spec, pairs, labels, graphs, feats = cpu_sample_workload(workload, s)
+        ds = RB.sparse_dataset(mods, pairs, labels.numpy(), spec['n_drug'], spec['n_dis'], feats[0], feats[1], graphs)
+        n_pairs, root = len(labels), None
     else:
-        sims = (th.tensor(R.feature_cosine_similarity(emb_d), dtype=th.float32),
-                th.tensor(R.feature_cosine_similarity(emb_s), dtype=th.float32))
-    return spec, enc, pairs, labels, graphs, (drug_feat, dis_feat, sims[0], sims[1]), fdim
+        s = scale
+        spec = synthetic.scaled(workload, s)
+        arrays = synthetic.mat_arrays(workload if s == 1 else spec, seed=mat_seed)
+        ds, root = RB.dense_dataset(mods, arrays, spec['k'])
+        n_pairs = int(ds.data_cv[0]['train'][2].numel())
+    per = RB.time_train(mods, ds, steps=steps, warmup=warmup, root=root)
+    dt = sum(per) / len(per)
+    edges = RB.aggregated_edges(ds)
+    out = {'value': round(edges / dt / 1e9, 6), 'unit': 'GE/s', 'cores': cores, 'kind': 'reference',
+           'sample': '%s at scale %.5g: %d drugs x %d diseases, %d scored pairs, same widths / k; %d iteration(s) of the '
+                     'UNMODIFIED reference train() (train.py:154-395 from %s, `import dgl` -> pure-torch stand-in oracle/dgl), '
+                     '%.2f s / iteration, torch threads=%d, cpu="%s"'
+                     % (workload, s, spec['n_drug'], spec['n_dis'], n_pairs, steps, RB.source(), dt, th.get_num_threads(), _cpu_model()),
+           'ms_per_step': round(dt * 1e3, 1), 'iters_per_sec_sample': round(1.0 / dt, 4), 'pairs': n_pairs,
+           'aggregated_edges_per_step_sample': int(edges)}
+    if sparse:
+        out['sample_scale'] = s
+    return out
 
 
-def cpu_reference(args, steps, warmup, budget_s=25.0, scale=None):
-    """Time `steps` full training iterations of the oracle port on all host cores. Unless --cpu-scale is
-    given the sample size is calibrated from a small probe so that (warmup + steps) fit `budget_s`."""
+def cpu_port(workload, scale, steps, warmup, budget_s, cpu_scale):
+    """Fallback when neither /root/reference nor the staged archive exists: the oracle's restatement of the iteration."""
     from dreamgnn_b200 import synthetic
     from dreamgnn_b200.model import Net
     from oracle import restate as R
     cores = os.cpu_count() or 1
-    th.set_num_threads(cores)
-    if scale is None:
-        scale = args.cpu_scale
-    if not scale:
-        sparse = args.workload.startswith('syn')
-        cap = args.scale / 40.0 if sparse else args.scale
-        probe_scale = min(cap, 0.004 if sparse else 0.25)
-        probe = cpu_reference(args, steps=1, warmup=0, scale=probe_scale)
-        per_pair = probe['ms_per_step'] / 1e3 / probe['pairs']
-        want_pairs = budget_s / max(steps + warmup, 1) / per_pair
-        full_pairs = probe['pairs'] / (probe_scale if sparse else probe_scale ** 2)
-        scale = min(cap, want_pairs / full_pairs if sparse else (want_pairs / full_pairs) ** 0.5)
-        scale = max(scale, probe_scale)
-    spec, enc, pairs, labels, graphs, feats, fdim = cpu_sample_workload(args.workload, scale)
-    w = dict(drug_feat=feats[0], dis_feat=feats[1], fdim_drug=fdim[0], fdim_disease=fdim[1])
+    sparse = synthetic.SHAPES[workload]['kind'] == 'sparse'
+    s = cpu_scale or (min(scale / 40.0, 0.01) if sparse else scale)
+    if not sparse:
+        raise RuntimeError('no reference available (build() stages oracle/_ref where /root/reference exists)')
+    spec, pairs, labels, graphs, feats = cpu_sample_workload(workload, s)
+    enc = R.enc_graph_from_pairs(pairs, labels.numpy(), spec['n_drug'], spec['n_dis'])
+    w = dict(drug_feat=feats[0], dis_feat=feats[1], fdim_drug=spec['f_drug'], fdim_disease=spec['f_dis'])
     th.manual_seed(1234)
-    sd = Net(synthetic.model_args(w, device='cpu')).state_dict()        # random init of the same architecture
-    P = {k: v.clone() for k, v in sd.items()}
+    P = {k: v.clone() for k, v in Net(synthetic.model_args(w, device='cpu')).state_dict().items()}
     for k in list(P):
         if '.ifc.' in k:
             P[k] = P[k.replace('.ifc.', '.ufc.')]
@@ -510,29 +757,20 @@ def cpu_reference(args, steps, warmup, budget_s=25.0, scale=None):
         v.requires_grad_(True)
     opt = th.optim.Adam(leaves, lr=0.002, weight_decay=1e-5)
     cfg = dict(layers=3, dropout=0.3, attention_dropout=0.1)
-    kept = sum(R.dropout_num_keep(len(s), 0.1) for s, _ in enc['edges'].values())
+    kept = sum(R.dropout_num_keep(len(a), 0.1) for a, _ in enc['edges'].values())
     knn_kept = sum(R.dropout_num_keep(len(g[2]), 0.1) for g in graphs)
-    agg_edges = 3 * 2 * kept + 4 * knn_kept        # GCMC: 3 layers x (fwd+bwd) x all 4 etypes; FGCN: 2 layers x (fwd+bwd)
+    edges = 3 * 2 * kept + 4 * knn_kept
+    f4 = (feats[0], feats[1], feats[0], feats[1])
     for _ in range(warmup):
-        R.train_iteration(P, opt, 0, enc, pairs, labels, graphs, feats, cfg)
+        R.train_iteration(P, opt, 0, enc, pairs, labels, graphs, f4, cfg)
     t0 = time.perf_counter()
     for _ in range(steps):
-        R.train_iteration(P, opt, 0, enc, pairs, labels, graphs, feats, cfg)
+        R.train_iteration(P, opt, 0, enc, pairs, labels, graphs, f4, cfg)
     dt = (time.perf_counter() - t0) / steps
-    cpu_model = ''
-    try:
-        with open('/proc/cpuinfo') as fh:
-            cpu_model = next((ln.split(':', 1)[1].strip() for ln in fh if ln.startswith('model name')), '')
-    except OSError:
-        pass
-    return {'value': round(agg_edges / dt / 1e9, 6), 'unit': 'GE/s', 'cores': cores, 'kind': 'port',
-            'sample': '%s at scale %.4g: %d drugs x %d diseases, %d scored pairs, same widths/k; %d step(s) of the '
-                      'full training iteration (oracle/restate.py = reference algorithm on a DGL stand-in), '
-                      '%.2f s/step, torch threads=%d, cpu="%s"'
-                      % (args.workload, scale, spec['n_drug'], spec['n_dis'], len(labels), steps, dt,
-                         th.get_num_threads(), cpu_model),
-            'ms_per_step': round(dt * 1e3, 1), 'iters_per_sec_sample': round(1.0 / dt, 4), 'pairs': len(labels),
-            'aggregated_edges_per_step_sample': int(agg_edges)}
+    return {'value': round(edges / dt / 1e9, 6), 'unit': 'GE/s', 'cores': cores, 'kind': 'port',
+            'sample': '%s at scale %.5g: %d drugs x %d diseases, %d scored pairs; oracle/restate.py port (no reference on this '
+                      'machine), %.2f s / iteration, cpu="%s"' % (workload, s, spec['n_drug'], spec['n_dis'], len(labels), dt, _cpu_model()),
+            'ms_per_step': round(dt * 1e3, 1), 'pairs': len(labels), 'aggregated_edges_per_step_sample': int(edges), 'sample_scale': s}
 
 
 def run_reference(args):
@@ -540,14 +778,20 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return                                       # rank 0 alone runs the CPU arm; others exit 0
-    base = cpu_reference(args, steps=args.steps, warmup=args.warmup, budget_s=150.0)
     from dreamgnn_b200 import synthetic
+    dense = synthetic.SHAPES[args.workload]['kind'] == 'dense'
+    steps = min(args.steps, 20) if dense else args.steps
+    base = cpu_reference(args.workload, args.scale, steps=steps, warmup=args.warmup, budget_s=150.0, cpu_scale=args.cpu_scale,
+                         mat_seed=synthetic.MAT_SEEDS.get(args.workload))
     spec = synthetic.scaled(args.workload, args.scale)
     out = {'impl': 'reference', 'metric': 'aggregated_edges_per_sec', 'value': base['value'], 'unit': 'GE/s',
-           'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': base['ms_per_step'],
+           'n_gpus': world, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': base['ms_per_step'],
+           'iters_per_sec': base['iters_per_sec_sample'] if 'iters_per_sec_sample' in base else round(1e3 / base['ms_per_step'], 4),
            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': '%s (%d drugs x %d diseases) -- timed on the bounded sample named in cpu_baseline'
-                                  % (args.workload, spec['n_drug'], spec['n_dis']),
+           'config': {'workload': '%s (%d drugs x %d diseases)%s' % (
+                          args.workload, spec['n_drug'], spec['n_dis'],
+                          '' if dense else ' -- timed on the bounded sample named in cpu_baseline; the B200 arm reports the same sample '
+                                           'in cpu_baseline.same_shape'),
                       'step': 'augmentation + forward + loss + backward + clip + Adam (train.py:250-300)'},
            'cpu_baseline': base,
            'e2e': {'value': base['value'], 'unit': 'GE/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -581,8 +825,13 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='syn20m', choices=['syn20m', 'syn400m', 'lrssl', 'gdataset', 'cdataset'])
     ap.add_argument('--scale', type=float, default=1.0, help='proportional shrink of the workload (tests)')
-    ap.add_argument('--cpu-scale', type=float, default=0.0, help='scale of the CPU sample (default: scale/40 for syn*)')
+    ap.add_argument('--cpu-scale', type=float, default=0.0, help='scale of the CPU sample (default: sized to a time budget, <= scale/40)')
+    ap.add_argument('--aug', default='default', choices=['default', 'full'],
+                    help="augmentation of the step: the reference's per-iteration default (edge_dropout feature_noise) or the "
+                         'full perturbation set (BASELINE config 3)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the lrssl / Gdataset / Cdataset lines of the default run')
+    ap.add_argument('--no-rows', action='store_true', help='N>1: skip the row-partitioned measurement after the fold-replica run')
     ap.add_argument('--eager', action='store_true', help='per-kernel launches instead of one CUDA-graph replay per step')
     ap.add_argument('--serial-aug', action='store_true',
                     help='CUDA-graph mode: keep the augmentation inside its own iteration (default: by size -- at the small '
@@ -590,20 +839,15 @@ def main():
     ap.add_argument('--pipeline-aug', action='store_true', help='force the pipelined augmentation at any size')
     ap.add_argument('--parallel-routes', action='store_true',
                     help='force the GCMC / FGCN routes (and the per-node-type halves) onto parallel graph branches at any size')
-    ap.add_argument('--cuda-graph', action='store_true',
-                    help='replay the whole training iteration from one captured CUDA graph (launch-bound small shapes)')
     ap.add_argument('--messages', default='f32', choices=['f32', 'bf16'],
                     help='storage of the gathered GCMC messages: f32 (1e-5 parity path, default) or bf16 (2e-2 path)')
     ap.add_argument('--parallel', default='folds', choices=['folds', 'rows'],
-                    help='N>1: independent fold-replicas (weak scaling, default) or one row-partitioned graph (strong)')
+                    help='N>1: independent fold-replicas (weak scaling, default; the row-partitioned graph is measured after '
+                         'it) or only the row-partitioned graph (strong)')
     args = ap.parse_args()
-    # default launch mode: one CUDA-graph replay per step for the single-graph-per-GPU workloads (the eager host loop
-    # enqueues ~800 launches per step at ~85 % of the device time and any host hiccup starves the GPU: measured
-    # random 100-300 ms steps); --eager keeps per-kernel launches. The row-partitioned path (NCCL inside) stays eager.
-    if args.parallel == 'rows' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
-        args.cuda_graph = False
-    elif not args.eager:
-        args.cuda_graph = True
+    # default launch mode: one CUDA-graph replay per step (the eager host loop enqueues ~800 launches per step at ~85 % of the
+    # device time and any host hiccup starves the GPU: measured random 100-300 ms steps); --eager keeps per-kernel launches
+    args.cuda_graph = not args.eager
     if args.eager and args.impl != 'reference':
         # per-kernel profile runs (ncu launch lists) execute the kernels of the timed configuration: the captured iteration
         # draws its edge dropout with the sort-free radix select, the plain eager loop would call th.randperm

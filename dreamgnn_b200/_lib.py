@@ -50,6 +50,12 @@ _SIGNATURES = {
     'dg_topk_rows_f64': (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P]),
     'dg_knn_graph_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'dg_knn_graph_from_neighbors': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    'dg_act_dropout_f32': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int, c_float, c_float, c_uint64, _P, _P]),
+    'dg_attention_fwd_f32': (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_float, c_uint64, _P, _P,
+                                     c_int64, _P, _P]),
+    'dg_attention_bwd_workspace_bytes': (c_size_t, [c_int64, c_int64]),
+    'dg_attention_bwd_f32': (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_float, c_uint64, _P, _P,
+                                     c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
     'dg_bench_read_rows': (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, _P, _P]),
 }
 

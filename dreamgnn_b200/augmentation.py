@@ -54,6 +54,18 @@ def _randperm(n, device):
     return th.randperm(n, device=device)
 
 
+def _coo_position(csr, base):
+    """For every slot of `csr` (the base CSR of a COO tensor or its transpose): the position of its entry in the tensor's
+    COO arrays. eid is that position, except for a tensor listed in slot order of `base` whose eids still name a parent's
+    entries (output of an edge dropout): there the forward CSR's slots are the positions and the transpose finds them
+    through the shared eid."""
+    if base.eid_is_slot or not base.slot_order:
+        return csr.eid
+    pos = th.empty(max(getattr(base, 'parent_nnz', 0), 1), dtype=th.int32, device=base.device)
+    pos[base.eid.long()] = th.arange(base.nnz, dtype=th.int32, device=base.device)
+    return pos[csr.eid.long()]
+
+
 def _sparse_from_csr(csr, shape, bwd=None):
     idx = th.stack([csr.rows().long(), csr.indices.long()])
     t = th.sparse_coo_tensor(idx, csr.vals, shape, device=csr.device, check_invariants=False)
@@ -86,7 +98,8 @@ class GraphAugmentation:
         if base.slot_order and not base.eid_is_slot:
             # output of an earlier dropout: its edge ids still name the grand-parent's entries;
             # renumber to this tensor's own COO positions (= slots) before drawing a new perm
-            pos = th.empty(int(base.eid.max()) + 1 if base.nnz else 1, dtype=th.int32, device=base.device)
+            # (sized from the parent's entry count kept on the CSR -- no device read)
+            pos = th.empty(max(getattr(base, 'parent_nnz', 0), base.nnz, 1), dtype=th.int32, device=base.device)
             pos[base.eid.long()] = th.arange(base.nnz, dtype=th.int32, device=base.device)
             t = base.transpose()
             nb = ops.CSR(base.indptr, base.indices, pos[base.eid.long()], base.vals, base.n_rows, base.n_cols)
@@ -98,12 +111,23 @@ class GraphAugmentation:
         k = num_keep_edges(n, dropout_rate)
         perm = _randperm(n, sparse_graph.device)
         flags = ops.keep_flags(n, [(perm, k, 0)], base.device)
-        return _sparse_from_csr(ops.csr_dropout(base, flags, k), sparse_graph.shape)
+        dropped = ops.csr_dropout(base, flags, k)
+        dropped.parent_nnz = dropped._t.parent_nnz = n            # eid values of the result name entries of this tensor
+        return _sparse_from_csr(dropped, sparse_graph.shape)
 
     @staticmethod
-    def add_random_edges(graph, add_rate=0.05, self_loops=False):
-        """augmentation.py:127-205: add max(1, int(E*rate)) new, distinct, not-yet-present edges per
-        relation. Candidates are drawn on device in batches; the first `num_add` valid ones win."""
+    def add_random_edges(graph, add_rate=0.05, self_loops=False, candidates=None):
+        """augmentation.py:127-205: per relation add num_add = max(1, int(E * rate)) new edges -- the first num_add
+        candidates, in draw order, among at most 10 * num_add uniform (src, dst) draws that are neither existing edges nor
+        repeats of an earlier accepted candidate (self-loops excluded when both endpoints are of one node type).
+
+        The reference walks the draws one by one in Python against a `set` of all existing edges; here all 10 * num_add
+        candidates are drawn at once on the device and filtered with three sorts / searches -- existing-edge membership by
+        binary search in the relation's sorted edge keys, first occurrence by a stable sort of the candidate keys, rank in
+        draw order by a prefix sum -- which selects exactly the edges the sequential walk accepts for the same draws. One
+        scalar (how many were accepted; it sizes the new edge list) is read back per relation: no host loop.
+        `candidates` = {canonical etype: (src, dst)} injects the draws (tests); default: torch's device generator (the
+        reference uses Python's `random`)."""
         if not isinstance(graph, HeteroGraph):
             return graph
         out = graph.clone()
@@ -115,70 +139,88 @@ class GraphAugmentation:
             if n == 0 or n_src == 0 or n_dst == 0:
                 continue
             num_add = max(1, int(n * add_rate))
+            m = num_add * 10                                       # augmentation.py:176
             src, dst = out.edges(etype=c)
-            have = src.long() * n_dst + dst.long()
-            new = th.empty(0, dtype=th.int64, device=device)
-            attempts, max_attempts = 0, num_add * 10               # augmentation.py:176
-            while new.numel() < num_add and attempts < max_attempts:
-                m = min(max(2 * (num_add - new.numel()), 64), max_attempts - attempts)
+            have = th.sort(src.long() * n_dst + dst.long()).values
+            if candidates is not None and c in candidates:
+                cs, cd = (th.as_tensor(x, device=device).long()[:m] for x in candidates[c])
+            else:
                 cs = th.randint(0, n_src, (m,), device=device)
                 cd = th.randint(0, n_dst, (m,), device=device)
-                attempts += m
-                ok = th.ones(m, dtype=th.bool, device=device)
-                if not self_loops and st == dt:
-                    ok &= cs != cd
-                key = cs * n_dst + cd
-                ok &= ~th.isin(key, have) & ~th.isin(key, new)
-                key = key[ok]
-                # first occurrence wins, draw order kept
-                uniq, inv = th.unique(key, return_inverse=True)
-                first = th.full((uniq.numel(),), key.numel(), dtype=th.int64, device=device)
-                first.scatter_reduce_(0, inv, th.arange(key.numel(), device=device), reduce='amin')
-                new = th.cat([new, key[th.sort(first).values]])[:num_add]
+            key = cs * n_dst + cd
+            pos = th.searchsorted(have, key).clamp_(max=n - 1)
+            ok = have[pos] != key                                  # not an existing edge
+            if not self_loops and st == dt:
+                ok &= cs != cd
+            # first occurrence among the candidates that could be accepted at all (a rejected draw does not block a later
+            # identical one -- it would be rejected again for the same reason)
+            order = th.sort(th.where(ok, key, th.full_like(key, -1)), stable=True).indices
+            skey = key[order]
+            dup = th.zeros_like(ok)
+            dup[order[1:]] = (skey[1:] == skey[:-1]) & ok[order[1:]] & ok[order[:-1]]
+            ok &= ~dup
+            rank = th.cumsum(ok.to(th.int64), 0)
+            take = ok & (rank <= num_add)
+            new = key[take]                                        # draw order; the one device -> host read sizes it
             if new.numel():
-                out.add_edges(new // n_dst, new % n_dst, etype=c)
+                out.add_edges(th.div(new, n_dst, rounding_mode='floor'), new % n_dst, etype=c)
         return out
 
     @staticmethod
-    def feature_noise(features, noise_scale=0.1):
-        """augmentation.py:208-241."""
+    def feature_noise(features, noise_scale=0.1, noise=None):
+        """augmentation.py:208-241. `noise` injects the N(0,1) draw (tests)."""
         if features is None:
             return None
         if not isinstance(features, th.Tensor):
             features = th.tensor(features, dtype=th.float32, device='cuda')
-        return th.add(features, th.randn_like(features), alpha=noise_scale)      # features + noise * scale, one pass
+        noise = th.randn_like(features) if noise is None else noise
+        return th.add(features, noise, alpha=noise_scale)                        # features + noise * scale, one pass
 
     @staticmethod
-    def sparse_graph_noise(graph, noise_scale=0.05):
-        """augmentation.py:244-273: noise on the stored values, clamped at 0; structure unchanged."""
+    def sparse_graph_noise(graph, noise_scale=0.05, noise=None):
+        """augmentation.py:244-273: noise on the stored values, clamped at 0; structure unchanged -- so the CSR and its
+        cached transpose are reused as they are and only the two value arrays are regathered (no sort).
+        `noise` injects the N(0,1) draw (tests)."""
         if not isinstance(graph, th.Tensor) or not graph.is_sparse:
             return graph
         values = graph._values()
-        noisy = th.clamp(values + th.randn_like(values) * noise_scale, min=0.0)
+        noise = th.randn_like(values) if noise is None else noise
+        noisy = th.clamp(values + noise * noise_scale, min=0.0)
         out = th.sparse_coo_tensor(graph._indices(), noisy, graph.shape, device=graph.device, check_invariants=False)
         base = adjacency_csr(graph)
-        vals = noisy.contiguous() if base.slot_order else noisy[base.eid.long()].contiguous()
-        csr = ops.CSR(base.indptr, base.indices, base.eid, vals, base.n_rows, base.n_cols)
-        csr.slot_order = base.slot_order       # transpose is rebuilt on demand with the new values
+        # position of slot s's entry in this tensor's COO arrays: s itself when the COO is in slot order, else eid[s] for
+        # a base graph (eid = COO position); a dropped graph's COO is always in slot order (_sparse_from_csr)
+        def regather(c):
+            return noisy.contiguous() if (c is base and base.slot_order) else noisy[_coo_position(c, base).long()].contiguous()
+        csr = ops.CSR(base.indptr, base.indices, base.eid, regather(base), base.n_rows, base.n_cols)
+        csr.slot_order, csr.eid_is_slot = base.slot_order, base.eid_is_slot
+        if base._t is not None:
+            t = base._t
+            ct = ops.CSR(t.indptr, t.indices, t.eid, regather(t), t.n_rows, t.n_cols)
+            ct.slot_order, ct.eid_is_slot = t.slot_order, t.eid_is_slot
+            csr._t, ct._t = ct, csr
         out._dg_csr = csr
         return out
 
     @staticmethod
-    def feature_masking(features, mask_rate=0.1):
-        """augmentation.py:276-308."""
+    def feature_masking(features, mask_rate=0.1, u=None):
+        """augmentation.py:276-308. `u` injects the U(0,1) draw (tests)."""
         if features is None:
             return None
         if not isinstance(features, th.Tensor):
             features = th.tensor(features, dtype=th.float32, device='cuda')
-        return features * (th.rand_like(features) > mask_rate)
+        u = th.rand_like(features) if u is None else u
+        return features * (u > mask_rate)
 
     @staticmethod
-    def mix_up_features(features, alpha=0.2):
-        """augmentation.py:311-337."""
+    def mix_up_features(features, alpha=0.2, indices=None, lam=None):
+        """augmentation.py:311-337. `indices` / `lam` inject the permutation and the Beta(alpha, alpha) draw (tests)."""
         if features is None or not isinstance(features, th.Tensor):
             return features
-        indices = th.randperm(features.size(0), device=features.device)
-        lam = np.random.beta(alpha, alpha)
+        if indices is None:
+            indices = th.randperm(features.size(0), device=features.device)
+        if lam is None:
+            lam = np.random.beta(alpha, alpha)
         return lam * features + (1 - lam) * features[indices]
 
 

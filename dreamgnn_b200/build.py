@@ -41,6 +41,16 @@ def _digest():
     return h.hexdigest()
 
 
+def kernel_digest(files):
+    """Digest of the named csrc files + compile flags: what an ncu capture of one kernel stays valid for."""
+    h = hashlib.sha256()
+    for f in sorted(files):
+        with open(os.path.join(CSRC, f), 'rb') as fh:
+            h.update(f.encode() + b'\0' + fh.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)

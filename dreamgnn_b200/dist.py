@@ -28,6 +28,28 @@ from . import ops
 from .graph import RelBlock
 
 
+# Optional collective log for bench.py: when PROFILE is a list every collective appends
+# (kind, payload bytes received / reduced on this rank, start event, end event) on the compute stream.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, kind, nbytes):
+        self.kind, self.nbytes = kind, int(nbytes)
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.nbytes, self.e0, self.e1))
+        return False
+
+
 def _world(group=None):
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -36,13 +58,34 @@ def _rank(group=None):
     return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
 
 
+# Forward collectives issued ahead of their consumer (`all_gather_rows(x, deferred=True)`): NCCL runs them on its own
+# stream, so kernels enqueued on the compute stream in the meantime (the other node type's projection / aggregation)
+# overlap the transfer; `wait_rows(t)` makes the compute stream wait right before the first read. Keyed by storage.
+_PENDING = {}
+
+
+def wait_rows(t):
+    """Block the current STREAM (not the host) until a deferred all-gather into `t` has landed. No-op otherwise."""
+    work = _PENDING.pop(t.data_ptr(), None) if isinstance(t, th.Tensor) else None
+    if work is not None:
+        with _Timed('all_gather_wait', 0):
+            work.wait()
+    return t
+
+
 class _AllGatherRows(th.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, deferred):
         world = _world()
         x = x.contiguous()
         out = th.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-        dist.all_gather_into_tensor(out, x)
+        if deferred and dist.get_backend() == 'nccl':
+            if PROFILE is not None:
+                PROFILE.append(('all_gather_bytes_deferred', out.numel() * out.element_size(), None, None))
+            _PENDING[out.data_ptr()] = dist.all_gather_into_tensor(out, x, async_op=True)
+            return out
+        with _Timed('all_gather', out.numel() * out.element_size()):
+            dist.all_gather_into_tensor(out, x)
         return out
 
     @staticmethod
@@ -53,29 +96,44 @@ class _AllGatherRows(th.autograd.Function):
         if dist.get_backend() == 'gloo':                      # gloo (CPU tests) has no reduce-scatter: all-reduce + slice
             g = g.clone()
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            return g[_rank() * n:(_rank() + 1) * n].clone()
+            return g[_rank() * n:(_rank() + 1) * n].clone(), None
         out = th.empty((n,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
-        dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
-        return out
+        with _Timed('reduce_scatter', g.numel() * g.element_size()):
+            dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
+        return out, None
 
 
 class _AllReduceSum(th.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         y = x.clone()
-        dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        with _Timed('all_reduce', y.numel() * y.element_size()):
+            dist.all_reduce(y, op=dist.ReduceOp.SUM)
         return y
 
     @staticmethod
     def backward(ctx, g):
         g = g.clone()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        with _Timed('all_reduce', g.numel() * g.element_size()):
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
         return g
 
 
-def all_gather_rows(x):
-    """[n_loc, ...] on every rank -> [world * n_loc, ...] (rank-major); backward = reduce-scatter(sum)."""
-    return _AllGatherRows.apply(x) if _world() > 1 else x
+def all_gather_rows(x, deferred=False):
+    """[n_loc, ...] on every rank -> [world * n_loc, ...] (rank-major); backward = reduce-scatter(sum).
+    `deferred`: enqueue the collective and return at once -- call `wait_rows` on the result before it is read."""
+    return _AllGatherRows.apply(x, deferred) if _world() > 1 else x
+
+
+def all_gather_plain(x):
+    """Non-differentiable all-gather of a small per-node vector (dropout-scaled cj: data, not a parameter)."""
+    if _world() == 1:
+        return x
+    x = x.contiguous()
+    out = th.empty((_world() * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    with _Timed('all_gather', out.numel() * out.element_size()):
+        dist.all_gather_into_tensor(out, x)
+    return out
 
 
 def all_reduce_sum(x):
@@ -236,9 +294,39 @@ class PartitionedPairs:
         self.partition = partition
 
 
+def gcmc_exchange(x, wstack, scale):
+    """First half of the distributed GCMC aggregation into one destination type: make the messages of ALL source nodes
+    available on this rank, in the rank-major layout the partitioned block's columns index
+    (row = owner * R * n_loc + r * n_loc + local id), moving as few bytes over NVLink as the layer allows:
+
+      * wide inputs (layer 0: 1024 / 768 features -> R x 344 messages): project the owned rows, pre-scale with
+        dropout(cj), all-gather the [R * n_loc, D_msg] messages;
+      * narrow inputs (layers 1-2: 128 -> R x 128): all-gather the [n_loc, 128] EMBEDDINGS (R times fewer bytes; the
+        per-relation dropout(cj) scales travel as [R * n_loc] floats), project after the gather -- every rank repeats the
+        small N x 128 x (R * 128) product -- and let the SpMM apply the scales.
+
+    Returns (gathered buffer or pending gather, src_scale for the SpMM or None, finish): `finish(buf)` completes the
+    exchange (waits for a deferred gather, projects if the embeddings were gathered) and returns the [world*R*n_loc, D]
+    message matrix. The collective is issued deferred, so work enqueued between `gcmc_exchange` and `finish` overlaps it."""
+    R, k_in, dp = wstack.shape
+    n_loc = x.shape[0]
+    world = _world()
+    if k_in < R * dp:                                   # gather embeddings, project afterwards
+        xg = all_gather_rows(x, deferred=True)          # [world * n_loc, k_in]
+        sg = all_gather_plain(scale.view(R, n_loc)).reshape(-1)      # [world, R, n_loc] = the buffer's row order
+
+        def finish(buf):
+            h = ops.project(wait_rows(buf), wstack)     # [R, world * n_loc, dp]
+            h = h.view(R, world, n_loc, dp).permute(1, 0, 2, 3).reshape(world * R * n_loc, dp)
+            return h
+        return xg, sg, finish
+    h = ops.project(x, wstack)                          # [R, n_loc, dp]
+    hg = all_gather_rows((h * scale.view(R, n_loc, 1)).reshape(R * n_loc, dp), deferred=True)
+    return hg, None, wait_rows
+
+
 def gcmc_aggregate(layer_scale, h, blk, ci):
-    """Distributed tail of GCMCLayer for one destination type: pre-scale the local messages with
-    dropout(cj), all-gather them, aggregate the owned rows."""
+    """One-shot form (messages already projected): pre-scale with dropout(cj), all-gather, aggregate the owned rows."""
     R, n_loc, dp = h.shape
     hg = all_gather_rows((h * layer_scale.view(R, n_loc, 1)).reshape(R * n_loc, dp))
     return ops.spmm(blk.csr, hg, src_scale=None, dst_scale=ci, tag='gcmc')
@@ -263,7 +351,8 @@ def all_reduce_gradients(params):
     if not grads:
         return
     flat = th.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    with _Timed('all_reduce_gradients', flat.numel() * flat.element_size()):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     off = 0
     for g in grads:
         n = g.numel()

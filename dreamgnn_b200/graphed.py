@@ -53,7 +53,7 @@ def _clone_csr(c):
     def one(x):
         n = ops.CSR(x.indptr.clone(), x.indices.clone(), x.eid.clone(), None if x.vals is None else x.vals.clone(),
                     x.n_rows, x.n_cols)
-        n.slot_order, n.eid_is_slot = x.slot_order, x.eid_is_slot
+        n.slot_order, n.eid_is_slot, n.parent_nnz = x.slot_order, x.eid_is_slot, x.parent_nnz
         return n
     n = one(c)
     if c._t is not None:

@@ -39,6 +39,17 @@ def _flat_f32(t):
     return t.reshape(-1).to(th.float32).contiguous()
 
 
+def _act_code(act):
+    """(code, slope) of an activation the fused act + dropout kernel implements, else None."""
+    if isinstance(act, nn.LeakyReLU):
+        return 'leaky', float(act.negative_slope)
+    if isinstance(act, nn.ReLU):
+        return 'relu', 0.0
+    if not isinstance(act, nn.Module) and act is not None and act(th.tensor(-2.0)).item() == -2.0:
+        return None, 0.0                                     # get_activation(None): the identity lambda
+    return False
+
+
 def adjacency_csr(adj):
     """CSR sidecar of a torch sparse-COO adjacency (cached on the tensor object). The COO may be
     uncoalesced (augmentation.py:124): duplicates simply stay separate entries of the row."""
@@ -154,6 +165,7 @@ class GCMCLayer(nn.Module):
                 sub['rev-%s' % rating] = GCMCGraphConv(movie_in_units, effective, True, device, dropout_rate)
         self.conv = HeteroGraphConv(sub, aggregate=agg)
         self.agg_act = get_activation(agg_act)
+        self._act_code = _act_code(self.agg_act)
         self.device = device
         self.reset_parameters()
 
@@ -196,34 +208,54 @@ class GCMCLayer(nn.Module):
             if c[2] not in seen:
                 seen.append(c[2])
 
-        def aggregate(dst_type):
-            """All relations into one node type: one batched projection, one SpMM."""
+        part = getattr(graph, 'partition', None)                     # row-partitioned graph: features hold the owned rows
+
+        def messages(dst_type):
+            """Projection operands of one destination type: (block, x, [R, in, Dp] weights, [R * N_src] dropout(cj) scales)."""
             blk = graph.block(dst_type)
             x = feats[blk.src_type]
-            part = getattr(graph, 'partition', None)             # row-partitioned graph: x holds the owned rows
             if part is None and x.size(0) != blk.n_src:
                 raise ValueError('%s features have %d rows for %d nodes' % (blk.src_type, x.size(0), blk.n_src))
             wstack = th.stack([_pad_cols(weights[c[1]], mult) for c in blk.etypes], dim=0)   # [R, in, Dp]
-            h = ops.project(x, wstack)                               # [R, N_src, Dp]: all relations' messages
-            dp = wstack.shape[2]
             cj = graph.nodes[blk.src_type].data['cj']
             scale = th.stack([_flat_f32(self.conv.mods[c[1]].dropout(cj)) for c in blk.etypes], dim=0).reshape(-1)
+            return blk, x, wstack, scale
+
+        def aggregate(dst_type):
+            """All relations into one node type: one batched projection, one SpMM."""
+            blk, x, wstack, scale = messages(dst_type)
+            h = ops.project(x, wstack)                               # [R, N_src, Dp]: all relations' messages
+            dp = wstack.shape[2]
             ci = _flat_f32(graph.nodes[dst_type].data['ci'])
-            if part is not None:
-                from . import dist as _dist
-                agg = _dist.gcmc_aggregate(scale, h, blk, ci)        # all-gather over NVLink + local SpMM
-            else:
-                if MESSAGE_DTYPE != th.float32:
-                    h = h.to(MESSAGE_DTYPE)
-                agg = ops.spmm(blk.csr, h.reshape(blk.num_rel * blk.n_src, dp), src_scale=scale, dst_scale=ci, tag='gcmc')
-            return agg
+            if MESSAGE_DTYPE != th.float32:
+                h = h.to(MESSAGE_DTYPE)
+            return ops.spmm(blk.csr, h.reshape(blk.num_rel * blk.n_src, dp), src_scale=scale, dst_scale=ci, tag='gcmc')
+
+        def aggregate_partitioned():
+            """Row-partitioned graph: both node types' exchanges are issued before either aggregation, so the all-gather
+            of one overlaps the projection / SpMM of the other (NVLink transfer under compute)."""
+            from . import dist as _dist
+            pend = {}
+            for t in seen:
+                blk, x, wstack, scale = messages(t)
+                pend[t] = (blk,) + _dist.gcmc_exchange(x, wstack, scale)
+            out = {}
+            for t in seen:
+                blk, buf, src_scale, finish = pend[t]
+                ci = _flat_f32(graph.nodes[t].data['ci'])
+                out[t] = ops.spmm(blk.csr, finish(buf), src_scale=src_scale, dst_scale=ci, tag='gcmc')
+            return out
 
         def tail(dst_type, agg):
             """Activation, dropout, output layer of one node type."""
             # The padded message columns (341 -> 344) are exactly zero through aggregation, activation and dropout, so
             # the tail runs on the padded width with zero weight columns appended to ifc / ufc: no slice copy forward,
             # no re-padding of the gradient backward, and the GEMM operands stay 16-byte aligned for TMA.
-            y = self.dropout(self.agg_act(agg))
+            code = self._act_code
+            if code is False:                                      # tanh / gelu / ...: no fused instance
+                y = self.dropout(self.agg_act(agg))
+            else:                                                  # activation + dropout in one launch (K7)
+                y = ops.act_dropout(agg, code[0], code[1], p=self.dropout.p, training=self.training)
             fc = self.ifc if dst_type == 'drug' else self.ufc
             w = _pad_cols(fc.weight, mult) if y.shape[1] != D else fc.weight
             return ops.linear(y, w, fc.bias)
@@ -235,7 +267,7 @@ class GCMCLayer(nn.Module):
             drug, dis = ops.branches([lambda: tail('drug', aggregate('drug')), lambda: tail('disease', aggregate('disease'))])
             return drug, dis
         # serial: the reference's dropout draw order (cj per etype in canonical order, then drug, then disease)
-        aggs = {t: aggregate(t) for t in seen}
+        aggs = aggregate_partitioned() if part is not None else {t: aggregate(t) for t in seen}
         return tail('drug', aggs['drug']), tail('disease', aggs['disease'])
 
 
@@ -294,7 +326,7 @@ class GCN(nn.Module):
 
     def _tail(self, support1, adj):
         x = self.gc1.aggregate(support1, adj, relu=True)          # spmm + bias + ReLU in one kernel
-        x = F.dropout(x, self.dropout, training=self.training)
+        x = ops.act_dropout(x, None, p=self.dropout, training=self.training)
         return self.gc2(x, adj)
 
     def forward(self, x, adj):
@@ -328,8 +360,8 @@ class FGCN(nn.Module):
             # the two node types as parallel stream branches (dropout draws then go drug, drug, disease, disease)
             def side(gcn, x, g_sim, g_feat, fusion):
                 e_sim, e_feat = gcn.forward_shared(x, [g_sim, g_feat])
-                fused = th.relu(ops.linear(th.cat([e_sim, e_feat], dim=1), fusion.weight, fusion.bias))
-                return F.dropout(fused, p=self.dropout, training=self.training), e_sim, e_feat
+                fused = ops.linear(th.cat([e_sim, e_feat], dim=1), fusion.weight, fusion.bias)
+                return ops.act_dropout(fused, 'relu', p=self.dropout, training=self.training), e_sim, e_feat
             (emb1, emb1_sim, emb1_feat), (emb2, emb2_sim, emb2_feat) = ops.branches([
                 lambda: side(self.FGCN_drug, drug_sim_feat, drug_graph, drug_feature_graph, self.drug_fusion),
                 lambda: side(self.FGCN_disease, disease_sim_feat, dis_graph, disease_feature_graph, self.disease_fusion)])
@@ -344,11 +376,10 @@ class FGCN(nn.Module):
         else:
             emb1_sim, emb1_feat = self.FGCN_drug.forward_shared(drug_sim_feat, [drug_graph, drug_feature_graph])
             emb2_sim, emb2_feat = self.FGCN_disease.forward_shared(disease_sim_feat, [dis_graph, disease_feature_graph])
-        fused_drug = th.relu(ops.linear(th.cat([emb1_sim, emb1_feat], dim=1), self.drug_fusion.weight, self.drug_fusion.bias))
-        fused_disease = th.relu(ops.linear(th.cat([emb2_sim, emb2_feat], dim=1), self.disease_fusion.weight,
-                                           self.disease_fusion.bias))
-        emb1 = F.dropout(fused_drug, p=self.dropout, training=self.training)
-        emb2 = F.dropout(fused_disease, p=self.dropout, training=self.training)
+        fused_drug = ops.linear(th.cat([emb1_sim, emb1_feat], dim=1), self.drug_fusion.weight, self.drug_fusion.bias)
+        fused_disease = ops.linear(th.cat([emb2_sim, emb2_feat], dim=1), self.disease_fusion.weight, self.disease_fusion.bias)
+        emb1 = ops.act_dropout(fused_drug, 'relu', p=self.dropout, training=self.training)        # ReLU + dropout, one launch
+        emb2 = ops.act_dropout(fused_disease, 'relu', p=self.dropout, training=self.training)
         return emb1, emb2, emb1_sim, emb1_feat, emb2_sim, emb2_feat
 
 
@@ -360,9 +391,24 @@ class Attention(nn.Module):
         self.project = nn.Sequential(nn.Linear(in_size, hidden_size), nn.Tanh(), nn.Linear(hidden_size, 1, bias=False))
         self.dropout = nn.Dropout(dropout_rate)
 
-    def forward(self, z):
+    def fuse(self, za, zb):
+        """`forward(th.stack((za, zb), dim=1))` without materialising the stack: one fused row kernel each way (K12)."""
+        lin1, lin2 = self.project[0], self.project[2]
+        if za.is_cuda and ops.attention_eligible(za, zb, lin1.weight):
+            out, beta = ops.attention_fuse(za, zb, lin1.weight, lin1.bias, lin2.weight, p=self.dropout.p, training=self.training)
+            return out, beta.unsqueeze(-1)
+        return self._forward_torch(th.stack((za, zb), dim=1))
+
+    def _forward_torch(self, z):
         beta = self.dropout(th.softmax(self.project(z), dim=1))
         return (beta * z).sum(1), beta
+
+    def forward(self, z):
+        if z.dim() == 3 and z.shape[1] == 2 and z.is_cuda and z.stride(2) == 1:
+            return self.fuse(z[:, 0], z[:, 1])
+        if not z.is_cuda:
+            raise RuntimeError('Attention needs CUDA tensors (no CPU fallback)')
+        return self._forward_torch(z)                              # K != 2 views: the reference's expression
 
 
 class MLPDecoder(nn.Module):

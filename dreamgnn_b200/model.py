@@ -48,7 +48,7 @@ class Net(nn.Module):
 
     def _fuse(self, topo, feat):
         """Shared two-view attention (model.py:93-97)."""
-        return self.attention(th.stack((topo, feat), dim=1))[0]
+        return self.attention.fuse(topo, feat)[0]
 
     def embed(self, enc_graph, drug_graph, drug_sim_feat, drug_feat, dis_graph, disease_sim_feat, dis_feat,
               drug_feature_graph=None, disease_feature_graph=None, Two_Stage=False):

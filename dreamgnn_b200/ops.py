@@ -76,7 +76,7 @@ class CSR:
     variants of one graph stay consistent.
     """
 
-    __slots__ = ('indptr', 'indices', 'eid', 'vals', 'n_rows', 'n_cols', '_t', 'slot_order', 'eid_is_slot')
+    __slots__ = ('indptr', 'indices', 'eid', 'vals', 'n_rows', 'n_cols', '_t', 'slot_order', 'eid_is_slot', 'parent_nnz')
 
     def __init__(self, indptr, indices, eid, vals, n_rows, n_cols):
         self.indptr, self.indices, self.eid, self.vals = indptr, indices, eid, vals
@@ -84,6 +84,7 @@ class CSR:
         self._t = None
         self.slot_order = False     # True when the owning COO tensor lists its entries in slot order
         self.eid_is_slot = False    # True when eid[s] == s (ids already name this tensor's own entries)
+        self.parent_nnz = 0         # edge-dropped CSR: entry count of the graph its eids refer to (sizes id lookups)
 
     @property
     def nnz(self):
@@ -344,6 +345,127 @@ def gram_common_loss(emb1, emb2):
     if emb1.shape != emb2.shape or not (_rows_ok(emb1) and _rows_ok(emb2)):
         raise ValueError('gram_common_loss: two [n, d] fp32 matrices with 16-byte aligned rows expected')
     return GramCommonLoss.apply(emb1, emb2)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused row kernels (csrc/fused.cu)
+# ------------------------------------------------------------------------------------------------
+ACT_CODES = {None: 0, 'identity': 0, 'leaky': 1, 'relu': 2}
+
+
+def fresh_seed(device):
+    """A dropout seed drawn on the device (no host sync; a captured CUDA graph gets a fresh one on every replay)."""
+    return th.randint(0, 2 ** 62, (1,), device=device, dtype=th.int64)
+
+
+def _seed_args(seed):
+    dev = seed if isinstance(seed, th.Tensor) else None
+    return (0 if dev is not None else int(seed)), dev
+
+
+class ActDropoutFunction(th.autograd.Function):
+    """y = dropout(act(x)) in one launch; the backward regenerates the keep mask from (seed, row, column group)."""
+
+    @staticmethod
+    def forward(ctx, x, act, slope, p, seed):
+        lib = L.load()
+        out = th.empty((x.shape[0], x.shape[1]), dtype=th.float32, device=x.device)
+        sv, sd = _seed_args(seed)
+        L.check(lib.dg_act_dropout_f32(x.data_ptr(), x.stride(0), None, 0, L.ptr(out), out.stride(0), x.shape[0], x.shape[1],
+                                       act, float(slope), float(p), sv, L.ptr(sd), L.stream()), 'act_dropout')
+        ctx.save_for_backward(x, sd)
+        ctx.cfg = (act, float(slope), float(p), sv)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, sd = ctx.saved_tensors
+        act, slope, p, sv = ctx.cfg
+        dy = dy if _rows_ok(dy) else dy.contiguous()
+        dx = th.empty((x.shape[0], x.shape[1]), dtype=th.float32, device=x.device)
+        L.check(lib.dg_act_dropout_f32(x.data_ptr(), x.stride(0), dy.data_ptr(), dy.stride(0), L.ptr(dx), dx.stride(0), x.shape[0],
+                                       x.shape[1], act, slope, p, sv, L.ptr(sd), L.stream()), 'act_dropout_bwd')
+        return dx, None, None, None, None
+
+
+def act_dropout(x, act=None, slope=0.1, p=0.0, training=True, seed=None):
+    """dropout(act(x)) for a 2-D fp32 CUDA matrix, act in {None, 'leaky', 'relu'} (layers.py:134-138, 247, 281-282).
+    Rows that the float4 kernel cannot address (width not a multiple of 4, unaligned) take the same expression in torch."""
+    if not x.is_cuda:
+        raise RuntimeError('dreamgnn_b200.act_dropout needs CUDA tensors (no CPU fallback)')
+    p = float(p) if training else 0.0
+    if act in (None, 'identity') and p == 0.0:
+        return x
+    if not (x.dim() == 2 and x.shape[0] > 0 and _rows_ok(x)):
+        y = x if act in (None, 'identity') else (th.nn.functional.leaky_relu(x, slope) if act == 'leaky' else th.relu(x))
+        return th.nn.functional.dropout(y, p, True) if p > 0 else y
+    if seed is None:
+        seed = fresh_seed(x.device) if p > 0 else 0
+    return ActDropoutFunction.apply(x, ACT_CODES[act], slope, p, seed)
+
+
+ATT_MAX_HIDDEN, ATT_MAX_WIDTH = 16, 256      # the backward's shared-memory reduction holds 9 x [16, d] floats
+
+
+class AttentionFunction(th.autograd.Function):
+    """Attention.forward (layers.py:324-338) over two views in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, za, zb, w1, b1, w2, p, seed):
+        lib = L.load()
+        n, d = za.shape
+        out = th.empty((n, d), dtype=th.float32, device=za.device)
+        beta = th.empty((n, 2), dtype=th.float32, device=za.device)
+        w1, b1, w2 = w1.contiguous(), b1.contiguous(), w2.reshape(-1).contiguous()
+        sv, sd = _seed_args(seed)
+        L.check(lib.dg_attention_fwd_f32(za.data_ptr(), za.stride(0), zb.data_ptr(), zb.stride(0), n, d, L.ptr(w1), L.ptr(b1),
+                                         L.ptr(w2), w1.shape[0], float(p), sv, L.ptr(sd), L.ptr(out), out.stride(0), L.ptr(beta),
+                                         L.stream()), 'attention_fwd')
+        ctx.save_for_backward(za, zb, w1, b1, w2, sd)
+        ctx.cfg = (float(p), sv)
+        ctx.set_materialize_grads(False)           # an unused beta output arrives as None, not as a zero matrix
+        return out, beta
+
+    @staticmethod
+    def backward(ctx, dout, dbeta):
+        lib = L.load()
+        za, zb, w1, b1, w2, sd = ctx.saved_tensors
+        p, sv = ctx.cfg
+        n, d = za.shape
+        h = w1.shape[0]
+        if dout is None:
+            dout = th.zeros((n, d), dtype=th.float32, device=za.device)
+        dout = dout if _rows_ok(dout) else dout.contiguous()
+        if dbeta is not None:
+            dbeta = dbeta.reshape(n, 2).contiguous()
+        dza = th.empty((n, d), dtype=th.float32, device=za.device) if ctx.needs_input_grad[0] else None
+        dzb = th.empty((n, d), dtype=th.float32, device=za.device) if ctx.needs_input_grad[1] else None
+        params = th.empty(16 * d + 32, dtype=th.float32, device=za.device)
+        ws = L.workspace(lib.dg_attention_bwd_workspace_bytes(n, d), za.device)
+        L.check(lib.dg_attention_bwd_f32(za.data_ptr(), za.stride(0), zb.data_ptr(), zb.stride(0), n, d, L.ptr(w1), L.ptr(b1),
+                                         L.ptr(w2), h, p, sv, L.ptr(sd), dout.data_ptr(), dout.stride(0), L.ptr(dbeta),
+                                         L.ptr(dza), d, L.ptr(dzb), d, L.ptr(params), L.ptr(ws), ws.numel(), L.stream()),
+                'attention_bwd')
+        dw1 = params[:16 * d].view(16, d)[:h]
+        db1 = params[16 * d:16 * d + h]
+        dw2 = params[16 * d + 16:16 * d + 16 + h].view(1, h)
+        return dza, dzb, dw1, db1, dw2, None, None
+
+
+def attention_eligible(za, zb, w1):
+    return (za.is_cuda and za.dtype == th.float32 and za.dim() == 2 and za.shape == zb.shape and za.shape[0] > 0
+            and _rows_ok(za) and _rows_ok(zb) and za.shape[1] <= ATT_MAX_WIDTH and w1.shape[0] <= ATT_MAX_HIDDEN)
+
+
+def attention_fuse(za, zb, w1, b1, w2, p=0.0, training=False, seed=None):
+    """(sum_k beta_k z_k [n, d], beta [n, 2]) for the two views za, zb; beta = dropout(softmax_k(w2 . tanh(W1 z_k + b1)))."""
+    if not za.is_cuda:
+        raise RuntimeError('dreamgnn_b200.attention_fuse needs CUDA tensors (no CPU fallback)')
+    p = float(p) if training else 0.0
+    if seed is None:
+        seed = fresh_seed(za.device) if p > 0 else 0
+    return AttentionFunction.apply(za, zb, w1, b1, w2, p, seed)
 
 
 # ------------------------------------------------------------------------------------------------

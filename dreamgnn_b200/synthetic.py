@@ -110,6 +110,49 @@ def dense_workload(spec, device, seed=0, train_fraction=0.9, sim_rank=32):
                 drug_sim_feat=sim_d.float(), dis_sim_feat=sim_s.float(), fdim_drug=n_d, fdim_disease=n_s, **graphs)
 
 
+MAT_SEEDS = {'lrssl': 0, 'gdataset': 1, 'cdataset': 2}
+
+
+def mat_arrays(shape, seed=None, sim_rank=32):
+    """A dense shape as a `.mat`-schema dict (data_loader.py:110-129: `didr` [N_dis x N_drug], `drug`, `disease`,
+    `drug_embed`, `disease_embed`, `Wrname`), seeded with numpy so that every consumer -- this package's DrugDataLoader on
+    the GPU, the reference's on the CPU -- reads the same dataset (SURVEY.md 8d config 1 generator)."""
+    import numpy as np
+    s = dict(SHAPES[shape]) if isinstance(shape, str) else dict(shape)
+    if s['kind'] != 'dense':
+        raise ValueError('mat_arrays: dense shapes only')
+    rng = np.random.default_rng((MAT_SEEDS.get(shape, 0) if isinstance(shape, str) else 0) if seed is None else seed)
+    n_d, n_s = s['n_drug'], s['n_dis']
+    cells = rng.choice(n_d * n_s, size=s['n_pos'], replace=False)
+    assoc = np.zeros((n_d, n_s), dtype=np.float64)
+    assoc[cells // n_s, cells % n_s] = 1.0
+
+    def sim(n):
+        x = rng.standard_normal((n, sim_rank))
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        m = (x @ x.T + 1.0) / 2.0
+        np.fill_diagonal(m, 1.0)
+        return m
+
+    names = np.empty((n_d, 1), dtype=object)
+    for i in range(n_d):
+        names[i, 0] = np.array(['DB%05d' % i])
+    return {'didr': assoc.T.copy(), 'drug': sim(n_d), 'disease': sim(n_s),
+            'drug_embed': rng.standard_normal((n_d, s['f_drug'])), 'disease_embed': rng.standard_normal((n_s, s['f_dis'])),
+            'Wrname': names}
+
+
+def write_mat(root, shape, loader_name='lrssl', seed=None):
+    """Write `<root>/raw_data/drug_data/<loader_name>/<loader_name>.mat` (the relative path DrugDataLoader reads)."""
+    import os
+    import scipy.io as sio
+    d = os.path.join(root, 'raw_data', 'drug_data', loader_name)
+    os.makedirs(d, exist_ok=True)
+    arrays = mat_arrays(shape, seed)
+    sio.savemat(os.path.join(d, loader_name + '.mat'), arrays)
+    return arrays
+
+
 def make_workload(spec, device, seed=1234):
     return sparse_workload(spec, device, seed) if spec['kind'] == 'sparse' else dense_workload(spec, device, seed)
 

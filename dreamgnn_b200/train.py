@@ -127,6 +127,18 @@ def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_param
     return total
 
 
+def make_train_state(dataset, cv, dev):
+    """The device-resident training inputs of fold `cv` exactly as train.py:172-204 prepares them."""
+    cv_data = dataset.data_cv[cv]
+    graphs = dataset.cv_specific_graphs[cv]
+    return TrainState(
+        cv_data['train'][0].int().to(dev), cv_data['train'][1].int().to(dev), cv_data['train'][2].to(dev),
+        graphs['drug_graph'].to(dev), graphs['disease_graph'].to(dev), graphs['drug_feature_graph'].to(dev),
+        graphs['disease_feature_graph'].to(dev), dataset.drug_feature.to(dev), dataset.disease_feature.to(dev),
+        th.as_tensor(dataset.drug_sim_features, dtype=th.float32).to(dev),
+        th.as_tensor(dataset.disease_sim_features, dtype=th.float32).to(dev))
+
+
 def train(args, dataset, cv):
     """Mirror of train.py:154-395: one fold. `dataset` must expose the reference loader's attributes
     (`drug_feature`, `disease_feature`, `*_feature_shape`, `drug_sim_features`, `disease_sim_features`,
@@ -138,14 +150,8 @@ def train(args, dataset, cv):
     args.fdim_disease = dataset.disease_feature_shape[0]
     args.rating_vals = dataset.cv_data_dict[cv][2]
     cv_data = dataset.data_cv[cv]
-    graphs = dataset.cv_specific_graphs[cv]
     dev = args.device
-    state = TrainState(
-        cv_data['train'][0].int().to(dev), cv_data['train'][1].int().to(dev), cv_data['train'][2].to(dev),
-        graphs['drug_graph'].to(dev), graphs['disease_graph'].to(dev), graphs['drug_feature_graph'].to(dev),
-        graphs['disease_feature_graph'].to(dev), dataset.drug_feature.to(dev), dataset.disease_feature.to(dev),
-        th.as_tensor(dataset.drug_sim_features, dtype=th.float32).to(dev),
-        th.as_tensor(dataset.disease_sim_features, dtype=th.float32).to(dev))
+    state = make_train_state(dataset, cv, dev)
     train_data_dict, test_data_dict = {'test': cv_data['train']}, {'test': cv_data['test']}
     model = Net(args=args).to(dev)
     if getattr(args, 'label_smoothing', 0.0) > 0:

@@ -233,6 +233,30 @@ DG_API int dg_knn_graph_from_neighbors(const int32_t* nbr, int64_t n, int k, int
                                 int32_t* row, int32_t* col, float* val, int32_t* nnz_out,
                                 void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
+/* ---- fused row kernels between the aggregations (csrc/fused.cu) ---------------------------- */
+/* y = dropout(act(x)) (dy == NULL) or its backward dx = dy * act'(x) * keep (dy != NULL), act: 0 identity, 1 LeakyReLU(slope),
+ * 2 ReLU. Replaces `agg_act` -> `self.dropout` before ufc / ifc (layers.py:134-138) and F.dropout in GCN / FGCN
+ * (layers.py:247, 281-282): one launch each way, the keep mask is a counter hash of (seed, row, column group) that the
+ * backward regenerates. seed_dev (device uint64, may be NULL) overrides seed (CUDA-graph replays). d % 4 == 0. */
+DG_API int dg_act_dropout_f32(const float* x, int64_t ldx, const float* dy, int64_t lddy, float* out, int64_t ldo,
+                       int64_t n_rows, int64_t d, int act, float slope, float p, uint64_t seed,
+                       const uint64_t* seed_dev, dg_stream_t stream);
+/* Attention.forward (layers.py:324-338) over K = 2 views given as two [n_rows, d] matrices (the reference stacks them):
+ * w_k = w2 . tanh(W1 z_k + b1), beta = dropout(softmax_k(w)), out = sum_k beta_k z_k; beta_out [n_rows, 2] optional.
+ * W1 [hidden, d] row-major (nn.Linear weight), hidden <= 16, d % 4 == 0, d <= 512. */
+DG_API int dg_attention_fwd_f32(const float* za, int64_t lda, const float* zb, int64_t ldb, int64_t n_rows, int64_t d,
+                         const float* w1, const float* b1, const float* w2, int hidden, float p, uint64_t seed,
+                         const uint64_t* seed_dev, float* out, int64_t ldo, float* beta_out, dg_stream_t stream);
+/* Backward: recomputes the forward from za / zb, writes dza / dzb (either may be NULL) and the parameter gradients packed
+ * as out_params = dW1 [16, d] (rows >= hidden zero) | db1 [16] | dw2 [16]; dbeta [n_rows, 2] (gradient of beta_out) may be
+ * NULL. Deterministic: per-warp register accumulators summed over warps and CTAs in fixed order. */
+DG_API size_t dg_attention_bwd_workspace_bytes(int64_t n_rows, int64_t d);
+DG_API int dg_attention_bwd_f32(const float* za, int64_t lda, const float* zb, int64_t ldb, int64_t n_rows, int64_t d,
+                         const float* w1, const float* b1, const float* w2, int hidden, float p, uint64_t seed,
+                         const uint64_t* seed_dev, const float* dout, int64_t lddo, const float* dbeta, float* dza,
+                         int64_t ldda, float* dzb, int64_t lddb, float* out_params, void* workspace,
+                         size_t workspace_bytes, dg_stream_t stream);
+
 /* ---- measurement support ------------------------------------------------------------------- */
 /* Read-bandwidth microbenchmark with the SpMM's access shape (scripts/l2_peak.py -> profiles/l2_peak.json): every warp
  * of a 148 * ctas_per_sm CTA grid reads `rows_per_warp` rows of `row_floats` fp32 from buf [n_rows, row_floats] with

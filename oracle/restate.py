@@ -304,6 +304,46 @@ def augment_default(enc_graph, knn_graphs, feats, rate=0.1, noise=0.05, sim_nois
     return g, coos, noisy
 
 
+def add_random_edges(src, dst, n_src, n_dst, add_rate, candidates, self_loops=False, same_type=False):
+    """augmentation.py:127-205 for one relation, with the random draws injected: `candidates` is the sequence of
+    (src, dst) pairs `random.randint` would produce, in draw order. num_add = max(1, int(E * add_rate)) (:152); at most
+    10 * num_add attempts (:176), each candidate counts as one attempt (:181-193); a candidate is accepted when it is not
+    an existing edge and not already accepted (:188). Returns the accepted (src, dst) in acceptance order -- they are
+    appended after the existing edges (:197-201)."""
+    num_edges = len(src)
+    if num_edges == 0 or n_src == 0 or n_dst == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    num_add = max(1, int(num_edges * add_rate))
+    have = set(zip(np.asarray(src).tolist(), np.asarray(dst).tolist()))
+    new, taken = [], set()
+    for attempt, (s, d) in enumerate(zip(np.asarray(candidates[0]).tolist(), np.asarray(candidates[1]).tolist())):
+        if len(new) >= num_add or attempt >= num_add * 10:
+            break
+        if not self_loops and same_type and s == d:
+            continue
+        if (s, d) not in have and (s, d) not in taken:
+            new.append((s, d))
+            taken.add((s, d))
+    a = np.asarray(new, dtype=np.int64).reshape(-1, 2)
+    return a[:, 0], a[:, 1]
+
+
+def sparse_graph_noise(values, noise, noise_scale):
+    """augmentation.py:244-273 with the N(0,1) draw injected: clamp(values + noise * scale, min=0); indices unchanged."""
+    return th.clamp(th.as_tensor(values) + th.as_tensor(noise) * noise_scale, min=0.0)
+
+
+def feature_masking(features, u, mask_rate):
+    """augmentation.py:276-308 with the U(0,1) draw injected: features * (u > mask_rate)."""
+    return th.as_tensor(features) * (th.as_tensor(u) > mask_rate)
+
+
+def mix_up_features(features, indices, lam):
+    """augmentation.py:311-337 with the permutation and the Beta(alpha, alpha) coefficient injected."""
+    f = th.as_tensor(features)
+    return lam * f + (1 - lam) * f[_idx(indices)]
+
+
 def make_adam_state(P):
     return {k: (th.zeros_like(v), th.zeros_like(v)) for k, v in P.items()}
 

@@ -182,3 +182,21 @@ def budget(ref_err_vs_exact, base=1e-5, slack=2.0):
     no fp32 implementation can be held closer to the reference than the reference is to the truth: there the bar is
     `slack` x the reference's own deviation."""
     return max(base, slack * ref_err_vs_exact)
+
+
+def tensor_class(name):
+    """Parameters that play the same role in different layers ('TGCN.0.att' / 'TGCN.2.att' -> 'att')."""
+    return '.'.join(p for p in name.split('.') if not p.isdigit() and p not in ('TGCN', 'FGCN'))
+
+
+def class_budgets(ref_errs, base=1e-5, slack=2.0):
+    """Per-tensor budgets from the reference's own deviations {name: err vs float64}. The few-element reduction tensors
+    (the [2, 2] basis-mixing coefficients `att`, the 16-element attention bias) are sums over 10^5..10^8 signed terms
+    whose rounding noise is a matter of luck per layer -- the reference's own fp32 run is 2.1e-5 off on TGCN.0.att, 6.8e-7
+    on TGCN.1.att and 3.1e-6 on TGCN.2.att at the lrssl shape -- so a tensor is held to the worst deviation the reference
+    shows on ANY tensor of its class, times `slack`, and never to less than the north star's 1e-5."""
+    worst = {}
+    for k, e in ref_errs.items():
+        c = tensor_class(k)
+        worst[c] = max(worst.get(c, 0.0), e)
+    return {k: max(base, slack * worst[tensor_class(k)]) for k in ref_errs}
