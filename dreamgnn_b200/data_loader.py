@@ -84,8 +84,8 @@ class DrugDataLoader(object):
         shared = {
             'drug_graph': GB.create_similarity_graph(self.drug_sim_features, k, dev, self._symm),
             'disease_graph': GB.create_similarity_graph(self.disease_sim_features, k, dev, self._symm),
-            'drug_feature_graph': GB.create_feature_similarity_graph(self.drug_embed, k, dev),
-            'disease_feature_graph': GB.create_feature_similarity_graph(self.disease_embed, k, dev),
+            'drug_feature_graph': GB.create_feature_similarity_graph(self.drug_embed, k, dev, symm=self._symm),
+            'disease_feature_graph': GB.create_feature_similarity_graph(self.disease_embed, k, dev, symm=self._symm),
         }
         for cv_idx in range(self._n_folds):
             train = self.cv_data_dict[cv_idx][0]

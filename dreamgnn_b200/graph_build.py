@@ -90,19 +90,97 @@ def knn_graph_from_topk(nbr):
     return _sparse_from_knn(csr, rows, nbr.shape[0])
 
 
-def create_similarity_graph(sim_matrix, k, device, symm=True):
-    """kNN graph of a given similarity matrix (float64, as scipy.io.loadmat hands it over)."""
-    if not symm:
-        raise NotImplementedError('only the symmetric branch (symm=True, the reference default) is built')
-    device = th.device(device)
+def _device_sim(sim_matrix, device):
     sim = th.as_tensor(np.ascontiguousarray(sim_matrix) if not isinstance(sim_matrix, th.Tensor) else sim_matrix)
-    sim = sim.to(device=device, dtype=th.float64).contiguous()
+    return sim.to(device=th.device(device), dtype=th.float64).contiguous()
+
+
+def _coo_from_keys(keys, vals, n, device):
+    """Sorted COO fp32 sparse tensor from int64 keys row * n + col (already unique and ascending)."""
+    idx = th.stack([th.div(keys, n, rounding_mode='floor'), keys % n])
+    return th.sparse_coo_tensor(idx, vals.to(th.float32), (n, n), device=device, check_invariants=False)
+
+
+def knn_graph_directed_from_topk(nbr):
+    """`self._symm` False (data_loader.py:302 skipped): D^-1 (A + I) of the directed kNN adjacency. Not on the training
+    path (one-off loader step): index work in torch on the device, float64 normalisation like utils.normalize."""
+    n, k = nbr.shape
+    dev = nbr.device
+    r = th.arange(n, device=dev, dtype=th.int64).repeat_interleave(k)
+    keys = th.cat([r * n + nbr.reshape(-1).long(), th.arange(n, device=dev, dtype=th.int64) * (n + 1)])
+    uniq, counts = th.unique(keys, return_counts=True)
+    val = counts.double()
+    row = th.div(uniq, n, rounding_mode='floor')
+    rowsum = th.zeros(n, dtype=th.float64, device=dev).index_add_(0, row, val)
+    r_inv = th.where(rowsum > 0, 1.0 / rowsum, th.zeros_like(rowsum))
+    return _coo_from_keys(uniq, r_inv[row] * val, n, dev)
+
+
+def create_similarity_graph(sim_matrix, k, device, symm=True):
+    """kNN graph of a given similarity matrix (float64, as scipy.io.loadmat hands it over): data_loader.py:278-310, both
+    values of `self._symm`."""
+    sim = _device_sim(sim_matrix, device)
     n = sim.shape[0]
     k_actual = min(k, n - 1)
-    return knn_graph_from_topk(ops.topk_rows(sim, k_actual))
+    nbr = ops.topk_rows(sim, k_actual)
+    return knn_graph_from_topk(nbr) if symm else knn_graph_directed_from_topk(nbr)
 
 
-def create_feature_similarity_graph(features, k, device, chunk_rows=8192):
+def _max_symmetrize(keys, vals, n):
+    """Elementwise max(A, A^T) of a non-negative sparse matrix given as (keys = row * n + col, float64 vals): the scipy
+    expression `adj + adj.T.multiply(adj.T > adj) - adj.multiply(adj.T > adj)` (utils.py:133, augmentation.py:395)."""
+    tk = (keys % n) * n + th.div(keys, n, rounding_mode='floor')
+    allk, allv = th.cat([keys, tk]), th.cat([vals, vals])
+    uniq, inv = th.unique(allk, return_inverse=True)
+    out = th.zeros(uniq.numel(), dtype=th.float64, device=keys.device).scatter_reduce_(0, inv, allv, reduce='amax', include_self=False)
+    return uniq, out
+
+
+def knn_graph(dis_mat, k, device):
+    """utils.knn_graph (utils.py:106-140; dead code in the reference -- imported at data_loader.py:30, never called -- kept
+    as part of the kNN builder's option set): binary, max-symmetrised kNN adjacency without self loops or normalisation,
+    as a sorted fp32 sparse COO tensor on the device (the reference returns a scipy matrix)."""
+    sim = _device_sim(dis_mat, device)
+    n = sim.shape[0]
+    k_actual = min(k, n - 1)
+    dev = sim.device
+    if k_actual <= 0:
+        i = th.arange(n, device=dev, dtype=th.int64)
+        return _coo_from_keys(i * (n + 1), th.ones(n, dtype=th.float64, device=dev), n, dev)
+    nbr = ops.topk_rows(sim, k_actual)
+    r = th.arange(n, device=dev, dtype=th.int64).repeat_interleave(k_actual)
+    keys, vals = _max_symmetrize(r * n + nbr.reshape(-1).long(), th.ones(r.numel(), dtype=th.float64, device=dev), n)
+    return _coo_from_keys(keys, vals, n, dev)
+
+
+def augmented_knn_graph(dis_mat, k, device, dropout_rate=0.1, add_noise=False, noise_scale=0.1, noise=None, keep=None):
+    """augmentation.augmented_knn_graph (augmentation.py:341-399; dead code in the reference): kNN graph -> optional value
+    noise clipped to [0.01, 1] -> random edge dropout -> max-symmetrise -> + I. `noise` / `keep` inject the draws (tests);
+    default: torch's device generator (the reference uses numpy's global one)."""
+    base = knn_graph(dis_mat, k, device).coalesce()
+    n = base.shape[0]
+    dev = base.device
+    idx, vals = base.indices(), base.values().double()
+    keys = idx[0] * n + idx[1]
+    if add_noise or noise is not None:
+        z = th.randn(vals.numel(), device=dev, dtype=th.float64) if noise is None else th.as_tensor(noise, device=dev).double()
+        vals = th.clamp(vals + z * noise_scale, 0.01, 1.0)
+    if keep is not None or dropout_rate > 0:
+        if keep is None:
+            num_keep = max(1, int(vals.numel() * (1 - dropout_rate)))
+            keep = th.randperm(vals.numel(), device=dev)[:num_keep]
+        keep = th.as_tensor(keep, device=dev).long()
+        keys, vals = keys[keep], vals[keep]
+    keys, vals = _max_symmetrize(keys, vals, n)
+    allk = th.cat([keys, th.arange(n, device=dev, dtype=th.int64) * (n + 1)])
+    allv = th.cat([vals, th.ones(n, dtype=th.float64, device=dev)])
+    uniq, inv = th.unique(allk, return_inverse=True)
+    out = th.zeros(uniq.numel(), dtype=th.float64, device=dev).index_add_(0, inv, allv)
+    idx = th.stack([th.div(uniq, n, rounding_mode='floor'), uniq % n])
+    return th.sparse_coo_tensor(idx, out, (n, n), device=dev, check_invariants=False)
+
+
+def create_feature_similarity_graph(features, k, device, chunk_rows=8192, symm=True):
     """kNN graph of the float64 cosine similarity of `features`; the N x N similarity is produced
     chunk by chunk (never resident as a whole) and reduced to top-k lists on the fly."""
     device = th.device(device)
@@ -118,8 +196,8 @@ def create_feature_similarity_graph(features, k, device, chunk_rows=8192):
     for r0 in range(0, n, chunk_rows):
         r1 = min(n, r0 + chunk_rows)
         nbr[r0:r1] = ops.topk_rows(th.mm(f[r0:r1], ft), k_actual)      # plain library DGEMM (cuBLAS)
-    return knn_graph_from_topk(nbr)
+    return knn_graph_from_topk(nbr) if symm else knn_graph_directed_from_topk(nbr)
 
 
-__all__ = ['generate_enc_graph', 'generate_dec_graph', 'create_similarity_graph',
-           'create_feature_similarity_graph', 'knn_graph_from_topk', 'HeteroGraph']
+__all__ = ['generate_enc_graph', 'generate_dec_graph', 'create_similarity_graph', 'create_feature_similarity_graph',
+           'knn_graph_from_topk', 'knn_graph_directed_from_topk', 'knn_graph', 'augmented_knn_graph', 'HeteroGraph']

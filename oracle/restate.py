@@ -105,10 +105,71 @@ def knn_graph_from_neighbors(nbr, n):
     return row, col, (r_inv[row] * val).astype(np.float32)
 
 
-def similarity_knn_graph(sim, k):
-    """data_loader.py:278-310 `_create_similarity_graph` (symm=True)."""
+def similarity_knn_graph(sim, k, symm=True):
+    """data_loader.py:278-310 `_create_similarity_graph`."""
     n = sim.shape[0]
+    if not symm:
+        return knn_graph_directed(topk_neighbors(sim, k), n)
     return knn_graph_from_neighbors(topk_neighbors(sim, k), n)
+
+
+def knn_graph_directed(nbr, n):
+    """data_loader.py:294-308 with `self._symm` False: A (ones at (i, nbr)) -> +I -> D^-1 A -> float32 COO, (row, col) sorted."""
+    k = nbr.shape[1]
+    r = np.repeat(np.arange(n, dtype=np.int64), k)
+    c = nbr.reshape(-1).astype(np.int64)
+    keys = np.concatenate([r * n + c, np.arange(n, dtype=np.int64) * (n + 1)])
+    uniq, counts = np.unique(keys, return_counts=True)
+    row, col = uniq // n, uniq % n
+    val = counts.astype(np.float64)
+    r_inv = np.power(np.bincount(row, weights=val, minlength=n), -1.0)
+    r_inv[np.isinf(r_inv)] = 0.
+    return row, col, (r_inv[row] * val).astype(np.float32)
+
+
+def max_symmetrize(row, col, val, n):
+    """`adj + adj.T.multiply(adj.T > adj) - adj.multiply(adj.T > adj)` (utils.py:133, augmentation.py:395) = the
+    elementwise maximum of A and A^T for non-negative entries. (row, col, val) sorted by (row, col), float64 values."""
+    row, col, val = np.asarray(row, dtype=np.int64), np.asarray(col, dtype=np.int64), np.asarray(val, dtype=np.float64)
+    keys = np.concatenate([row * n + col, col * n + row])
+    vals = np.concatenate([val, val])
+    order = np.lexsort((-vals, keys))                       # per key: largest value first
+    keys, vals = keys[order], vals[order]
+    first = np.concatenate([[True], keys[1:] != keys[:-1]])
+    return keys[first] // n, keys[first] % n, vals[first]
+
+
+def knn_graph_binary(sim, k):
+    """utils.py:106-140 `knn_graph` (dead code in the reference; the kNN builder's option set): ones at the k_actual =
+    min(k, n - 1) largest entries of each row, max-symmetrised; no self loops added, no normalisation; float32."""
+    n = sim.shape[0]
+    k_actual = min(k, n - 1)
+    if k_actual <= 0:
+        i = np.arange(n, dtype=np.int64)
+        return i, i, np.ones(n, dtype=np.float32)
+    nbr = topk_neighbors(sim, k)
+    r = np.repeat(np.arange(n, dtype=np.int64), k_actual)
+    row, col, val = max_symmetrize(r, nbr.reshape(-1), np.ones(r.size), n)
+    return row, col, val.astype(np.float32)
+
+
+def augmented_knn_graph(sim, k, keep=None, noise=None, noise_scale=0.1):
+    """augmentation.py:341-399 with the random draws injected: `noise` ~ N(0,1) per stored entry of the kNN graph (in
+    (row, col) order; None = add_noise False), `keep` = indices of the entries kept by the dropout (None = rate 0).
+    values + noise * scale clipped to [0.01, 1] -> keep -> max-symmetrise -> + I. Returns (row, col, val float64)."""
+    n = sim.shape[0]
+    row, col, val = knn_graph_binary(sim, k)
+    val = val.astype(np.float64)
+    if noise is not None:
+        val = np.clip(val + np.asarray(noise, dtype=np.float64) * noise_scale, 0.01, 1.0)
+    if keep is not None:
+        keep = np.asarray(keep)
+        row, col, val = row[keep], col[keep], val[keep]
+    row, col, val = max_symmetrize(row, col, val, n)
+    keys = np.concatenate([row * n + col, np.arange(n, dtype=np.int64) * (n + 1)])
+    vals = np.concatenate([val, np.ones(n)])
+    uniq, inv = np.unique(keys, return_inverse=True)
+    return uniq // n, uniq % n, np.bincount(inv, weights=vals)
 
 
 def feature_cosine_similarity(features):

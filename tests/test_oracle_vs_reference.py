@@ -82,3 +82,43 @@ def test_forward_backward_live(live):
     for k, p in net.named_parameters():
         if p.grad is not None:
             assert H.rel_err(P[k].grad, p.grad) <= 1e-5, k
+
+
+def test_knn_option_set_matches_reference():
+    """a14 + the symm=False loader branch: oracle restatements vs the reference's own functions (utils.knn_graph and
+    augmentation.augmented_knn_graph are dead code there, but part of the kNN builder's option set)."""
+    import scipy.sparse as sp
+    mods = rr.import_reference()
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((40, 6))
+    sim = x @ x.T
+    for k in (0, 3, 7, 60):
+        want = sp.coo_matrix(mods['utils'].knn_graph(sim, k)).tocsr()
+        want.sort_indices()
+        want = want.tocoo()
+        row, col, val = R.knn_graph_binary(sim, k)
+        np.testing.assert_array_equal(row, want.row)
+        np.testing.assert_array_equal(col, want.col)
+        np.testing.assert_array_equal(val, want.data.astype(np.float32))
+    # augmented version: replay numpy's global generator for the injected draws
+    base_row, base_col, base_val = R.knn_graph_binary(sim, 4)
+    np.random.seed(3)
+    want = sp.coo_matrix(mods['augmentation'].augmented_knn_graph(sim, 4, dropout_rate=0.2, add_noise=True, noise_scale=0.1)).tocsr()
+    want.sort_indices()
+    want = want.tocoo()
+    np.random.seed(3)
+    noise = np.random.normal(0, 1.0, len(base_val))               # normal(0, s, n) == s * normal(0, 1, n) in numpy's generator
+    keep = np.random.choice(len(base_val), max(1, int(len(base_val) * 0.8)), replace=False)
+    row, col, val = R.augmented_knn_graph(sim, 4, keep=keep, noise=noise, noise_scale=0.1)
+    np.testing.assert_array_equal(row, want.row)
+    np.testing.assert_array_equal(col, want.col)
+    np.testing.assert_allclose(val, want.data, rtol=1e-12, atol=0)
+    # loader with symm=False
+    loader = object.__new__(mods['data_loader'].DrugDataLoader)
+    loader._symm = False
+    t = loader._create_similarity_graph(sim, 4)
+    gr, gc, gv = H.canon_coo(t._indices()[0].numpy(), t._indices()[1].numpy(), t._values().numpy())
+    row, col, val = R.similarity_knn_graph(sim, 4, symm=False)
+    np.testing.assert_array_equal(row, gr)
+    np.testing.assert_array_equal(col, gc)
+    np.testing.assert_array_equal(val, gv)
