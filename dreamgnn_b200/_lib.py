@@ -56,7 +56,7 @@ _SIGNATURES = {
     'dg_attention_bwd_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'dg_attention_bwd_f32': (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_float, c_uint64, _P, _P,
                                      c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
-    'dg_bench_read_rows': (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, _P, _P]),
+    'dg_bench_read_rows': (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -193,11 +193,11 @@ class GraphAugmentation:
         def regather(c):
             return noisy.contiguous() if (c is base and base.slot_order) else noisy[_coo_position(c, base).long()].contiguous()
         csr = ops.CSR(base.indptr, base.indices, base.eid, regather(base), base.n_rows, base.n_cols)
-        csr.slot_order, csr.eid_is_slot = base.slot_order, base.eid_is_slot
+        csr.slot_order, csr.eid_is_slot, csr.parent_nnz = base.slot_order, base.eid_is_slot, base.parent_nnz
         if base._t is not None:
             t = base._t
             ct = ops.CSR(t.indptr, t.indices, t.eid, regather(t), t.n_rows, t.n_cols)
-            ct.slot_order, ct.eid_is_slot = t.slot_order, t.eid_is_slot
+            ct.slot_order, ct.eid_is_slot, ct.parent_nnz = t.slot_order, t.eid_is_slot, t.parent_nnz
             csr._t, ct._t = ct, csr
         out._dg_csr = csr
         return out

@@ -11,7 +11,6 @@ namespace dg {
 namespace {
 
 constexpr int kBenchThreads = 256;
-constexpr int kInFlight = 4;                    // rows in flight per warp (the SpMM instances keep 3-4)
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du;
@@ -20,6 +19,7 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   return x;
 }
 
+template <int kInFlight>                       // rows in flight per warp (the SpMM instances keep 4-8)
 __global__ void __launch_bounds__(kBenchThreads)
 bench_read_kernel(const float4* __restrict__ buf, int64_t n_rows, int row_f4, int64_t rows_per_warp, int random,
                   float* __restrict__ sink) {
@@ -50,14 +50,23 @@ bench_read_kernel(const float4* __restrict__ buf, int64_t n_rows, int row_f4, in
 }  // namespace dg
 
 extern "C" int dg_bench_read_rows(const float* buf, int64_t n_rows, int64_t row_floats, int64_t rows_per_warp, int random,
-                                  int ctas_per_sm, float* sink, dg_stream_t stream) {
+                                  int ctas_per_sm, int rows_in_flight, float* sink, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(buf != nullptr && sink != nullptr, "null pointer");
   DG_REQUIRE(n_rows > 0 && row_floats > 0 && row_floats % 4 == 0 && rows_per_warp > 0, "bad shape");
-  DG_REQUIRE(rows_per_warp % kInFlight == 0, "rows_per_warp must be a multiple of 4");
+  DG_REQUIRE(rows_in_flight == 2 || rows_in_flight == 4 || rows_in_flight == 8 || rows_in_flight == 16, "rows_in_flight: 2, 4, 8 or 16");
+  DG_REQUIRE(rows_per_warp % rows_in_flight == 0, "rows_per_warp must be a multiple of rows_in_flight");
   DG_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 8, "ctas_per_sm out of range");
-  bench_read_kernel<<<kNumSM * ctas_per_sm, kBenchThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(buf), n_rows, static_cast<int>(row_floats / 4), rows_per_warp, random, sink);
+  const float4* b4 = reinterpret_cast<const float4*>(buf);
+  const int f4 = static_cast<int>(row_floats / 4);
+  const unsigned grid = kNumSM * ctas_per_sm;
+  cudaStream_t st = as_stream(stream);
+  switch (rows_in_flight) {
+    case 2: bench_read_kernel<2><<<grid, kBenchThreads, 0, st>>>(b4, n_rows, f4, rows_per_warp, random, sink); break;
+    case 4: bench_read_kernel<4><<<grid, kBenchThreads, 0, st>>>(b4, n_rows, f4, rows_per_warp, random, sink); break;
+    case 8: bench_read_kernel<8><<<grid, kBenchThreads, 0, st>>>(b4, n_rows, f4, rows_per_warp, random, sink); break;
+    default: bench_read_kernel<16><<<grid, kBenchThreads, 0, st>>>(b4, n_rows, f4, rows_per_warp, random, sink); break;
+  }
   DG_CHECK_LAUNCH("bench_read_rows");
   return DG_OK;
 }

@@ -28,6 +28,10 @@ from .utils import get_activation, to_etype_name
 # feature storage for the gathered GCMC messages: th.float32 (1e-5 parity path) or th.bfloat16
 # (2e-2 path: bf16 storage, fp32 accumulate)
 MESSAGE_DTYPE = th.float32
+# message width is padded (zero weight columns) to a multiple of this many elements; 0 = the vector width (4 fp32 / 8 bf16).
+# 32 fp32 = whole 128-byte lines per gathered row (341 -> 352 instead of 344): see DESIGN.md on the d = 344 SpMM
+import os as _os
+MESSAGE_PAD = int(_os.environ.get('DG_MSG_PAD', '0'))
 
 
 def _pad_cols(t, mult):
@@ -202,7 +206,7 @@ class GCMCLayer(nn.Module):
         feats = {'drug': drug_feat, 'disease': dis_feat}
         weights = self._relation_weights()
         D = self.msg_units
-        mult = 8 if MESSAGE_DTYPE == th.bfloat16 else 4
+        mult = MESSAGE_PAD or (8 if MESSAGE_DTYPE == th.bfloat16 else 4)
         seen = []
         for c in graph.canonical_etypes:                 # blocks in the reference's etype order
             if c[2] not in seen:

@@ -260,10 +260,11 @@ DG_API int dg_attention_bwd_f32(const float* za, int64_t lda, const float* zb, i
 /* ---- measurement support ------------------------------------------------------------------- */
 /* Read-bandwidth microbenchmark with the SpMM's access shape (scripts/l2_peak.py -> profiles/l2_peak.json): every warp
  * of a 148 * ctas_per_sm CTA grid reads `rows_per_warp` rows of `row_floats` fp32 from buf [n_rows, row_floats] with
- * 128-bit L1-bypassing loads, 4 rows in flight; rows are consecutive across warps (random = 0) or pseudo-random
- * (random = 1). Bytes read = 148 * ctas_per_sm * 8 warps * rows_per_warp * row_floats * 4. Not on the product path. */
+ * 128-bit L1-bypassing loads, `rows_in_flight` (2 / 4 / 8 / 16) rows in flight; rows are consecutive across warps
+ * (random = 0) or pseudo-random (random = 1). Bytes read = 148 * ctas_per_sm * 8 warps * rows_per_warp * row_floats * 4.
+ * Not on the product path. */
 DG_API int dg_bench_read_rows(const float* buf, int64_t n_rows, int64_t row_floats, int64_t rows_per_warp, int random,
-                       int ctas_per_sm, float* sink, dg_stream_t stream);
+                       int ctas_per_sm, int rows_in_flight, float* sink, dg_stream_t stream);
 
 #ifdef __cplusplus
 }
