@@ -32,7 +32,7 @@ def num_keep_edges(num_edges, dropout_rate):
 # below this the select buys nothing measurable: its 17 small launches against a sort of a few hundred thousand pairs
 # (A/B on one box: lrssl 2.46 ms / iteration with randperm vs 2.64 with the select, Gdataset 1.93 vs 1.79 -- inside the
 # run-to-run spread of these latency-chain iterations), so the sampler whose kept sets match the reference's stays
-SELECT_MIN_EDGES = 1 << 20
+SELECT_MIN_EDGES = int(os.environ.get('DG_SELECT_MIN_EDGES', str(1 << 20)))
 
 
 def _randperm(n, device):

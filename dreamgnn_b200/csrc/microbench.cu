@@ -27,18 +27,30 @@ bench_read_kernel(const float4* __restrict__ buf, int64_t n_rows, int row_f4, in
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * kBenchThreads + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * kBenchThreads) >> 5;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // row ids cost a handful of integer instructions (multiply-shift range reduction / add-and-wrap): the loop must stay
+  // load-bound even for 512-byte rows
+  const uint32_t nr = static_cast<uint32_t>(n_rows);
+  const uint32_t salt = mix32(static_cast<uint32_t>(warp) * 0x9e3779b1u + 0x7f4a7c15u);
+  uint32_t seq = static_cast<uint32_t>(warp % n_rows);
+  const uint32_t step = static_cast<uint32_t>(n_warps % n_rows);
   for (int64_t i = 0; i < rows_per_warp; i += kInFlight) {
-    int64_t row[kInFlight];
+    const float4* rp[kInFlight];
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u) {
-      const int64_t k = i + u;
-      row[u] = random ? static_cast<int64_t>(mix32(static_cast<uint32_t>(warp * 0x9e3779b1u) ^ mix32(static_cast<uint32_t>(k)))) % n_rows
-                      : (k * n_warps + warp) % n_rows;
+      uint32_t r;
+      if (random) {
+        r = __umulhi(mix32(salt ^ static_cast<uint32_t>(i + u)), nr);
+      } else {
+        r = seq;
+        seq += step;
+        if (seq >= nr) seq -= nr;
+      }
+      rp[u] = buf + static_cast<int64_t>(r) * row_f4;
     }
     for (int c = lane; c < row_f4; c += 32) {
       float4 v[kInFlight];
 #pragma unroll
-      for (int u = 0; u < kInFlight; ++u) v[u] = ldg_f4_stream(buf + row[u] * row_f4 + c);
+      for (int u = 0; u < kInFlight; ++u) v[u] = ldg_f4_stream(rp[u] + c);
 #pragma unroll
       for (int u = 0; u < kInFlight; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
@@ -53,7 +65,7 @@ extern "C" int dg_bench_read_rows(const float* buf, int64_t n_rows, int64_t row_
                                   int ctas_per_sm, int rows_in_flight, float* sink, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(buf != nullptr && sink != nullptr, "null pointer");
-  DG_REQUIRE(n_rows > 0 && row_floats > 0 && row_floats % 4 == 0 && rows_per_warp > 0, "bad shape");
+  DG_REQUIRE(n_rows > 0 && n_rows < (1ll << 31) && row_floats > 0 && row_floats % 4 == 0 && rows_per_warp > 0, "bad shape");
   DG_REQUIRE(rows_in_flight == 2 || rows_in_flight == 4 || rows_in_flight == 8 || rows_in_flight == 16, "rows_in_flight: 2, 4, 8 or 16");
   DG_REQUIRE(rows_per_warp % rows_in_flight == 0, "rows_per_warp must be a multiple of rows_in_flight");
   DG_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 8, "ctas_per_sm out of range");

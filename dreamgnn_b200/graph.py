@@ -296,7 +296,11 @@ class HeteroGraph:
             raise DGLError('only update_all(copy_u, sum) is implemented (layers.py:229-232)')
         c = self.to_canonical_etype(etype)
         h = self._ndata[c[0]][message_func.u]
-        self._ndata[c[2]][reduce_func.out] = ops.spmm(self.etype_csr(c), h)
+        d = h.shape[1]
+        if d % 4:                                          # the kernel gathers 16-byte vectors: zero-pad odd widths
+            h = th.nn.functional.pad(h, (0, (-d) % 4))
+        out = ops.spmm(self.etype_csr(c), h)
+        self._ndata[c[2]][reduce_func.out] = out[:, :d] if out.shape[1] != d else out
 
     def apply_edges(self, func, etype=None):
         c = self.to_canonical_etype(etype)

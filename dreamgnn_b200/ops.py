@@ -723,7 +723,7 @@ def knn_graph_from_neighbors(nbr):
 # ------------------------------------------------------------------------------------------------
 import os as _os
 
-GEMM_MIN_MACS = 1 << 26          # below this the launch + operand split costs more than it saves: cuBLAS via torch
+GEMM_MIN_MACS = int(_os.environ.get('DG_GEMM_MIN_MACS', str(1 << 26)))   # below this: cuBLAS via torch (launch + operand split cost)
 
 
 def gemm_backend():

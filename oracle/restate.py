@@ -270,23 +270,33 @@ def graph_convolution(P, prefix, x, coo):
     return out + b if b is not None else out
 
 
-def gcn(P, prefix, x, coo, p=0.0, training=False):
+def _relu(pre, mask=None):
+    """F.relu, or -- when the checker matches masks -- `pre * mask` with the ReLU mask of the implementation under test: a
+    gradient is a discontinuous function of that mask, so an entry whose pre-activation lies within fp32 rounding of zero
+    makes the comparison ill-posed unless both sides differentiate through the same mask (tests/shapes.py)."""
+    return F.relu(pre) if mask is None else pre * th.as_tensor(mask).to(pre.dtype)
+
+
+def gcn(P, prefix, x, coo, p=0.0, training=False, mask=None):
     """layers.py:245-249 `GCN.forward`."""
-    h = F.dropout(F.relu(graph_convolution(P, prefix + 'gc1.', x, coo)), p, training)
+    h = F.dropout(_relu(graph_convolution(P, prefix + 'gc1.', x, coo), mask), p, training)
     return graph_convolution(P, prefix + 'gc2.', h, coo)
 
 
 def fgcn(P, prefix, drug_graph, drug_sim_feat, dis_graph, dis_sim_feat,
-         drug_feature_graph=None, dis_feature_graph=None, p=0.0, training=False):
-    """layers.py:260-285 `FGCN.forward` -> (emb1, emb2, emb1_sim, emb1_feat, emb2_sim, emb2_feat)."""
-    e1s = gcn(P, prefix + 'FGCN_drug.', drug_sim_feat, drug_graph, p, training)
-    e2s = gcn(P, prefix + 'FGCN_disease.', dis_sim_feat, dis_graph, p, training)
+         drug_feature_graph=None, dis_feature_graph=None, p=0.0, training=False, masks=None):
+    """layers.py:260-285 `FGCN.forward` -> (emb1, emb2, emb1_sim, emb1_feat, emb2_sim, emb2_feat). `masks` (checker only):
+    ReLU masks keyed 'gc1.drug.sim', 'gc1.disease.sim', 'gc1.drug.feat', 'gc1.disease.feat', 'fusion.drug', 'fusion.disease'."""
+    m = masks or {}
+    e1s = gcn(P, prefix + 'FGCN_drug.', drug_sim_feat, drug_graph, p, training, m.get('gc1.drug.sim'))
+    e2s = gcn(P, prefix + 'FGCN_disease.', dis_sim_feat, dis_graph, p, training, m.get('gc1.disease.sim'))
     if drug_feature_graph is None or dis_feature_graph is None:
         return e1s, e2s, e1s, None, e2s, None
-    e1f = gcn(P, prefix + 'FGCN_drug.', drug_sim_feat, drug_feature_graph, p, training)
-    e2f = gcn(P, prefix + 'FGCN_disease.', dis_sim_feat, dis_feature_graph, p, training)
-    f1 = th.relu(F.linear(th.cat([e1s, e1f], 1), P[prefix + 'drug_fusion.weight'], P[prefix + 'drug_fusion.bias']))
-    f2 = th.relu(F.linear(th.cat([e2s, e2f], 1), P[prefix + 'disease_fusion.weight'], P[prefix + 'disease_fusion.bias']))
+    e1f = gcn(P, prefix + 'FGCN_drug.', drug_sim_feat, drug_feature_graph, p, training, m.get('gc1.drug.feat'))
+    e2f = gcn(P, prefix + 'FGCN_disease.', dis_sim_feat, dis_feature_graph, p, training, m.get('gc1.disease.feat'))
+    f1 = _relu(F.linear(th.cat([e1s, e1f], 1), P[prefix + 'drug_fusion.weight'], P[prefix + 'drug_fusion.bias']), m.get('fusion.drug'))
+    f2 = _relu(F.linear(th.cat([e2s, e2f], 1), P[prefix + 'disease_fusion.weight'], P[prefix + 'disease_fusion.bias']),
+               m.get('fusion.disease'))
     return F.dropout(f1, p, training), F.dropout(f2, p, training), e1s, e1f, e2s, e2f
 
 
@@ -308,8 +318,8 @@ def mlp_decoder(P, prefix, src, dst, drug_feat, dis_feat, p=0.0, training=False)
 
 def net_forward(P, enc_graph, dec_pairs, drug_graph, drug_sim_feat, drug_feat,
                 dis_graph, dis_sim_feat, dis_feat, drug_feature_graph=None, dis_feature_graph=None,
-                layers=3, act='leaky', dropout=0.0, attention_dropout=0.0, training=False):
-    """model.py:60-103 `Net.forward` -> (pred [E,1], drug_out, drug_sim_out, dis_out, dis_sim_out)."""
+                layers=3, act='leaky', dropout=0.0, attention_dropout=0.0, training=False, relu_masks=None):
+    """model.py:60-103 `Net.forward` -> (pred [E,1], drug_out, drug_sim_out, dis_out, dis_sim_out). `relu_masks`: see fgcn."""
     drug_out = dis_out = None
     for i in range(layers):                                   # model.py:67-76
         d_o, s_o = gcmc_layer(P, 'TGCN.%d.' % i, enc_graph, drug_feat, dis_feat, act, dropout, training)
@@ -317,7 +327,7 @@ def net_forward(P, enc_graph, dec_pairs, drug_graph, drug_sim_feat, drug_feat,
         dis_out = s_o if i == 0 else dis_out + s_o / float(i + 1)
         drug_feat, dis_feat = d_o, s_o
     drug_sim_out, dis_sim_out = fgcn(P, 'FGCN.', drug_graph, drug_sim_feat, dis_graph, dis_sim_feat,
-                                     drug_feature_graph, dis_feature_graph, dropout, training)[:2]
+                                     drug_feature_graph, dis_feature_graph, dropout, training, relu_masks)[:2]
     drug_feats, _ = attention(P, 'attention.', th.stack([drug_out, drug_sim_out], 1), attention_dropout, training)
     dis_feats, _ = attention(P, 'attention.', th.stack([dis_out, dis_sim_out], 1), attention_dropout, training)
     pred = mlp_decoder(P, 'decoder.', dec_pairs[0], dec_pairs[1], drug_feats, dis_feats, dropout, training)

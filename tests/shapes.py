@@ -122,7 +122,45 @@ def oracle_params(sd, dtype=th.float32, requires_grad=False):
     return P
 
 
-def oracle_forward(ds, enc, knn, sd, split='train', dtype=th.float32, training=False, requires_grad=False):
+import contextlib
+
+
+@contextlib.contextmanager
+def capture_relu_masks():
+    """Record the ReLU masks of the product path's FGCN route while a forward runs (dropout p = 0): the four gc1
+    activations (spmm + bias + ReLU in one kernel) and the two fusion activations, keyed as oracle/restate.py:fgcn expects.
+    The float64 oracle then differentiates through the SAME masks (restate._relu), which makes the gradient comparison
+    well-posed: the handful of entries (out of ~10^6) whose pre-activation is within fp32 rounding of zero would otherwise
+    each move a downstream gradient norm by ~1e-4."""
+    from dreamgnn_b200 import ops
+    rec = {'spmm': [], 'act': []}
+    real_spmm, real_act = ops.spmm, ops.act_dropout
+
+    def spmm(csr, x, src_scale=None, dst_scale=None, bias=None, relu=False, tag='spmm'):
+        out = real_spmm(csr, x, src_scale, dst_scale, bias, relu, tag)
+        if relu:
+            rec['spmm'].append((out.detach() > 0).cpu())
+        return out
+
+    def act_dropout(x, act=None, slope=0.1, p=0.0, training=True, seed=None):
+        out = real_act(x, act, slope, p, training, seed)
+        if act == 'relu':
+            rec['act'].append((out.detach() > 0).cpu())
+        return out
+    ops.spmm, ops.act_dropout = spmm, act_dropout
+    masks = {}
+    try:
+        yield masks
+    finally:
+        ops.spmm, ops.act_dropout = real_spmm, real_act
+    if len(rec['spmm']) == 4 and len(rec['act']) == 2:          # FGCN.forward order: drug (sim, feat), disease (sim, feat); fusions
+        masks.update({'gc1.drug.sim': rec['spmm'][0], 'gc1.drug.feat': rec['spmm'][1], 'gc1.disease.sim': rec['spmm'][2],
+                      'gc1.disease.feat': rec['spmm'][3], 'fusion.drug': rec['act'][0], 'fusion.disease': rec['act'][1]})
+    else:
+        raise AssertionError('unexpected FGCN call pattern: %d fused-ReLU SpMMs, %d ReLU act_dropouts' % (len(rec['spmm']), len(rec['act'])))
+
+
+def oracle_forward(ds, enc, knn, sd, split='train', dtype=th.float32, training=False, requires_grad=False, relu_masks=None):
     P = oracle_params(sd, dtype, requires_grad)
     pairs, _ = ds['split'][split]
     g = dict(enc[split])
@@ -131,7 +169,7 @@ def oracle_forward(ds, enc, knn, sd, split='train', dtype=th.float32, training=F
     knn_t = [(r, c, th.as_tensor(v).to(dtype), n) for r, c, v, n in knn]
     out = R.net_forward(P, g, pairs, knn_t[0], ds['drug_sim'].to(dtype), ds['drug_feat'].to(dtype), knn_t[1],
                         ds['dis_sim'].to(dtype), ds['dis_feat'].to(dtype), knn_t[2], knn_t[3], layers=NET['layers'],
-                        training=training)
+                        training=training, relu_masks=relu_masks)
     return P, out
 
 
@@ -164,14 +202,20 @@ def load_shape_golden(name):
         return {k: z[k] for k in z.files}
 
 
-def oracle_loss_and_grads(ds, enc, knn, sd, dtype):
+def oracle_loss_and_grads(ds, enc, knn, sd, dtype, relu_masks=None):
     """Training-mode forward (all dropout p = 0) + loss (train.py:286-294) + backward of the oracle in `dtype`.
     Returns (outputs, loss, {parameter name: gradient})."""
-    P, out = oracle_forward(ds, enc, knn, sd, dtype=dtype, training=True, requires_grad=True)
+    P, out = oracle_forward(ds, enc, knn, sd, dtype=dtype, training=True, requires_grad=True, relu_masks=relu_masks)
     loss = R.training_loss(out, th.tensor(ds['split']['train'][1]).to(dtype))
     loss.backward()
     grads = {k: v.grad for k, v in P.items() if v.grad is not None}
     return [o.detach() for o in out], float(loss.detach()), grads
+
+
+def mask_disagreements(masks, ref_masks):
+    """(entries whose ReLU mask differs, total entries) between the implementation's masks and the oracle's."""
+    diff = sum(int((th.as_tensor(masks[k]) != th.as_tensor(ref_masks[k])).sum()) for k in masks)
+    return diff, sum(int(th.as_tensor(m).numel()) for m in masks.values())
 
 
 def budget(ref_err_vs_exact, base=1e-5, slack=2.0):
@@ -189,14 +233,30 @@ def tensor_class(name):
     return '.'.join(p for p in name.split('.') if not p.isdigit() and p not in ('TGCN', 'FGCN'))
 
 
-def class_budgets(ref_errs, base=1e-5, slack=2.0):
-    """Per-tensor budgets from the reference's own deviations {name: err vs float64}. The few-element reduction tensors
-    (the [2, 2] basis-mixing coefficients `att`, the 16-element attention bias) are sums over 10^5..10^8 signed terms
-    whose rounding noise is a matter of luck per layer -- the reference's own fp32 run is 2.1e-5 off on TGCN.0.att, 6.8e-7
-    on TGCN.1.att and 3.1e-6 on TGCN.2.att at the lrssl shape -- so a tensor is held to the worst deviation the reference
-    shows on ANY tensor of its class, times `slack`, and never to less than the north star's 1e-5."""
+TINY = 16            # elements
+TINY_BASE = 3e-5
+
+
+def class_budgets(ref_errs, numel=None, base=1e-5, slack=4.0):
+    """Per-tensor gradient budgets {name: bound on the norm-wise error against the float64 value}.
+
+      * the north star's 1e-5 wherever an fp32 evaluation can meet it;
+      * `slack` x the reference's OWN fp32 deviation from the float64 value where that is larger. slack = 4 is the measured
+        ratio of the rounding error of the tensor-core 3xTF32 products to that of an fp32 FMA chain (2.2e-6 against 5.7e-7
+        norm-wise on the layer-0 projection): on a tensor whose conditioning amplifies the reference's
+        5.7e-7 to, say, 1.2e-5 (the weight of the 1 %-of-edges relation, TGCN.0.conv.mods.1.weight), the same conditioning
+        amplifies 2.2e-6 to 4.8e-5, and no reassociation-free bound tighter than that exists;
+      * the deviation is taken as the worst over the tensors of the same class (same role in different layers): the
+        few-element reduction tensors -- the [2, 2] basis-mixing coefficients `att`, the 16-element attention bias -- are sums
+        over 10^5..10^8 signed terms whose rounding noise is a matter of luck per layer (the reference's own fp32 run is
+        2.1e-5 off on TGCN.0.att, 6.8e-7 on TGCN.1.att, 3.1e-6 on TGCN.2.att at the lrssl shape);
+      * tensors of at most 16 elements never get less than 3e-5 for the same reason."""
     worst = {}
     for k, e in ref_errs.items():
         c = tensor_class(k)
         worst[c] = max(worst.get(c, 0.0), e)
-    return {k: max(base, slack * worst[tensor_class(k)]) for k in ref_errs}
+    out = {}
+    for k in ref_errs:
+        b = base if numel is None or numel.get(k, TINY + 1) > TINY else max(base, TINY_BASE)
+        out[k] = max(b, slack * worst[tensor_class(k)])
+    return out
