@@ -252,6 +252,8 @@ def measure(ctx, workload, scale, steps, warmup, aug='default', cuda_graph=True,
             launch_mode = 'one CUDA-graph replay per step' + (
                 ' (augmentation of step i+1 on a parallel branch of step i)' if getattr(step, 'staged', None) is not None else '')
         except Exception as e:                               # noqa: BLE001 -- an augmentation that cannot be captured
+            import traceback
+            traceback.print_exc()
             th.cuda.synchronize()
             step, cuda_graph = eager_step, False
             launch_mode = 'eager launches (capture failed: %s)' % str(e).splitlines()[0][:120]
@@ -605,13 +607,15 @@ def run_b200(args):
                                   'cpu_ms_per_step': base['ms_per_step'], 'ratio': round(base['ms_per_step'] / g['ms_per_step'], 1),
                                   'e2e_ratio': round(base['ms_per_step'] / g['e2e_ms_per_step'], 1), 'same_config': True}
         out['cpu_baseline'] = base
-        if args.workload == 'syn20m' and args.scale == 1.0 and not args.no_extra:
+        if (args.workload == 'syn20m' and args.scale == 1.0 and not args.no_extra) or args.extra:
             out['extra_workloads'] = extra_workloads(ctx, args)
     if world > 1 and not args.no_rows:
         try:
             out['row_partitioned'] = measure_rows(ctx, args.workload, args.scale, max(3, min(args.steps, 10)), 3,
                                                   single_gpu_ms=single_ms)
         except Exception as e:                                   # noqa: BLE001 -- never lose the main line
+            import traceback
+            traceback.print_exc()
             out['row_partitioned'] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:300])}
     if rank == 0:
         emit(out)
@@ -644,6 +648,8 @@ def extra_workloads(ctx, args):
                                  'augmentation_rebuild_ms': f['augmentation_rebuild_ms'], 'launch': f['launch_mode']}
             out[name] = e
         except Exception as ex:                                  # noqa: BLE001 -- never lose the main line
+            import traceback
+            traceback.print_exc()
             out[name] = {'error': '%s: %s' % (type(ex).__name__, str(ex).splitlines()[0][:300])}
     return out
 
@@ -831,6 +837,7 @@ def main():
                          'full perturbation set (BASELINE config 3)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the lrssl / Gdataset / Cdataset lines of the default run')
+    ap.add_argument('--extra', action='store_true', help='add the lrssl / Gdataset / Cdataset lines to any run')
     ap.add_argument('--no-rows', action='store_true', help='N>1: skip the row-partitioned measurement after the fold-replica run')
     ap.add_argument('--eager', action='store_true', help='per-kernel launches instead of one CUDA-graph replay per step')
     ap.add_argument('--serial-aug', action='store_true',

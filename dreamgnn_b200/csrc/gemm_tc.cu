@@ -374,8 +374,13 @@ static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, int64_t batch) {
   // the tensor-core accumulator truncates when it aligns addends, so its error grows ~linearly with the
   // number of accumulated terms: cap one TMEM accumulation at 64 k-blocks (K = 2048) and let the fp32
   // split-K reduction (round-to-nearest) combine the pieces. Measured: 1.8e-6 rel at K=1024, 5e-6 at K=5000.
-  constexpr int kMaxKbPerAccum = 64;
-  if ((g.nkb + splits - 1) / splits > kMaxKbPerAccum) splits = (g.nkb + kMaxKbPerAccum - 1) / kMaxKbPerAccum;
+  // Long-K products that are split anyway (weight gradients: K = number of nodes, small output) take shorter chains of
+  // 24 k-blocks (K = 768): at K = 100 000 the 2048-long chains measured 1.5e-5 norm-wise against float64 on dW of the
+  // layer-0 projection (tests/test_gpu_syn20m.py), above the 1e-5 bar; their partial tiles are small, so the extra
+  // splits cost ~0.1 ms per product.
+  constexpr int kMaxKbPerAccum = 64, kMaxKbLongK = 24;
+  const int cap = (splits > 1 && g.nkb > 4 * kMaxKbPerAccum) ? kMaxKbLongK : kMaxKbPerAccum;
+  if ((g.nkb + splits - 1) / splits > cap) splits = (g.nkb + cap - 1) / cap;
   g.kb_per_split = (g.nkb + splits - 1) / splits;
   g.splits = (g.nkb + g.kb_per_split - 1) / g.kb_per_split;  // no empty split
   g.partial_elems = g.splits > 1 ? static_cast<size_t>(batch) * g.splits * M * N : 0;

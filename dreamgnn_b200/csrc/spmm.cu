@@ -23,6 +23,7 @@ struct LoadF32 {
   using Elem = float;
   using Raw = float4;
   __device__ static __forceinline__ Raw load(const Elem* p) { return ldg_f4_stream(reinterpret_cast<const float4*>(p)); }
+  __device__ static __forceinline__ Raw load_l1(const Elem* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
   __device__ static __forceinline__ void unpack(const Raw& t, float (&v)[kVec]) {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
@@ -33,6 +34,7 @@ struct LoadBF16 {
   using Elem = __nv_bfloat16;
   using Raw = uint4;
   __device__ static __forceinline__ Raw load(const Elem* p) { return ldg_u4_stream(reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ Raw load_l1(const Elem* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
   __device__ static __forceinline__ void unpack(const Raw& t, float (&v)[kVec]) {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
@@ -44,11 +46,16 @@ struct LoadBF16 {
 };
 
 // L2 prefetch of the 128-byte lines [first, last] of one gathered row, spread over `lanes` lanes (sub = lane's slot)
+// (kL1: into L1 instead -- the demand loads of that instance allocate in / hit L1, so the L2 -> SM latency of the next
+// group is covered too, again without holding registers)
+template <bool kL1 = false>
 __device__ __forceinline__ void prefetch_row_l2(const void* row, unsigned bytes, int sub, int lanes) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(row);
   const uintptr_t first = a >> 7, last = (a + bytes - 1) >> 7;
-  for (uintptr_t ln = first + sub; ln <= last; ln += lanes)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(ln << 7) : "memory");
+  for (uintptr_t ln = first + sub; ln <= last; ln += lanes) {
+    if (kL1) asm volatile("prefetch.global.L1 [%0];" ::"l"(ln << 7) : "memory");
+    else asm volatile("prefetch.global.L2 [%0];" ::"l"(ln << 7) : "memory");
+  }
 }
 
 // Prefetch distance in groups of kUnroll rows (0 = off). DG_SPMM_PREFETCH overrides the default for experiments.
@@ -62,7 +69,18 @@ static int spmm_prefetch_distance() {
   return v;
 }
 
-template <typename L, int NCHUNK, int kUnroll, bool kWeighted, int kMinBlocks, bool kPf>
+// kPf: 0 = no prefetch, 1 = L2 prefetch (streaming demand loads), 2 = L1 prefetch (demand loads through L1)
+static int spmm_prefetch_l1() {          // DG_SPMM_PF_L1=<distance in groups>: L1-prefetch instance (0 / unset = off)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DG_SPMM_PF_L1");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+
+template <typename L, int NCHUNK, int kUnroll, bool kWeighted, int kMinBlocks, int kPf>
 __global__ void __launch_bounds__(256, kMinBlocks)
 spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ vals,
                 const float* __restrict__ src_scale, const float* __restrict__ dst_scale,
@@ -125,7 +143,7 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
       for (int q0 = kUnroll; q0 < pf_lo; q0 += kUnroll) {
         const int q = q0 + pf_r;
         const int jj = __shfl_sync(kFull, j, q & 31);
-        if (q < cnt) prefetch_row_l2(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
+        if (q < cnt) prefetch_row_l2<kPf == 2>(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
       }
     }
     for (; t + kUnroll <= cnt; t += kUnroll) {
@@ -135,10 +153,10 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
         const int q = t + pf_lo + pf_r;                 // batch position of the row this lane helps to prefetch
         if (t + pf_lo + kUnroll <= 32) {                // window inside this batch (warp-uniform branch)
           const int jj = __shfl_sync(kFull, j, q & 31);
-          if (q < cnt) prefetch_row_l2(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
+          if (q < cnt) prefetch_row_l2<kPf == 2>(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
         } else if (t + pf_lo >= 32) {                   // window inside the next batch: its indices landed long ago
           const int jj = __shfl_sync(kFull, j_nx, (q - 32) & 31);
-          if (base + q < end) prefetch_row_l2(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
+          if (base + q < end) prefetch_row_l2<kPf == 2>(x + static_cast<int64_t>(jj) * ldx + slab_c0, pf_bytes, pf_sub, kPfLanes);
         }
       }
 #pragma unroll
@@ -147,7 +165,7 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
         const typename L::Elem* xr = x + static_cast<int64_t>(jj) * ldx + col0;
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c)
-          if (live[c]) buf[u][c] = L::load(xr + c * 32 * V);
+          if (live[c]) buf[u][c] = (kPf == 2) ? L::load_l1(xr + c * 32 * V) : L::load(xr + c * 32 * V);
       }
       if (kWeighted) {
 #pragma unroll
@@ -346,15 +364,19 @@ static int launch_spmm(const int* indptr, const int* indices, const float* vals,
   const int64_t blocks = (warps + 7) / 8;
   if (blocks > 0x7fffffffLL) { set_error("spmm: grid too large"); return DG_ERR_INVALID_ARGUMENT; }
   int pf = (flags & DG_SPMM_PREFETCH) ? spmm_prefetch_distance() : 0;
+  const int l1 = spmm_prefetch_l1();                                   // experiment: prefetch into L1 (any operand size)
+  if (l1 > 0) pf = l1;
   if (pf * kUnroll > 32 - kUnroll) pf = (32 - kUnroll) / kUnroll;      // the window stays within one batch + the next
 #define DG_SPMM_LAUNCH(W, P)                                                                                   \
   spmm_csr_kernel<L, NCHUNK, kUnroll, W, kMinBlocks, P><<<static_cast<unsigned>(blocks), 256, 0, st>>>(          \
       indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags, pf)
   const bool weighted = vals || src_scale;
-  if (pf > 0) {
-    if (weighted) DG_SPMM_LAUNCH(true, true); else DG_SPMM_LAUNCH(false, true);
+  if (pf > 0 && l1 > 0) {
+    if (weighted) DG_SPMM_LAUNCH(true, 2); else DG_SPMM_LAUNCH(false, 2);
+  } else if (pf > 0) {
+    if (weighted) DG_SPMM_LAUNCH(true, 1); else DG_SPMM_LAUNCH(false, 1);
   } else {
-    if (weighted) DG_SPMM_LAUNCH(true, false); else DG_SPMM_LAUNCH(false, false);
+    if (weighted) DG_SPMM_LAUNCH(true, 0); else DG_SPMM_LAUNCH(false, 0);
   }
 #undef DG_SPMM_LAUNCH
   DG_CHECK_LAUNCH("spmm_csr");
