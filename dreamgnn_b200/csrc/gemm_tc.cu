@@ -378,8 +378,13 @@ static GemmPlan plan_gemm(int64_t M, int64_t N, int64_t K, int64_t batch) {
   // 24 k-blocks (K = 768): at K = 100 000 the 2048-long chains measured 1.5e-5 norm-wise against float64 on dW of the
   // layer-0 projection (tests/test_gpu_syn20m.py), above the 1e-5 bar; their partial tiles are small, so the extra
   // splits cost ~0.1 ms per product.
-  constexpr int kMaxKbPerAccum = 64, kMaxKbLongK = 24;
-  const int cap = (splits > 1 && g.nkb > 4 * kMaxKbPerAccum) ? kMaxKbLongK : kMaxKbPerAccum;
+  // Small outputs (<= 2 M elements: the real-dataset shapes, every weight gradient) take chains of 8 k-blocks (K = 256):
+  // their partial tiles cost nothing, the extra splits spread a handful of tiles over more SMs, and the truncation bias
+  // (~6e-8 of the running sum per accumulate) stays ~1e-6 -- at the lrssl shape the 763-long chains left the FGCN weight
+  // gradients at 1.0-1.1e-5 against float64 (tests/test_gpu_shapes.py).
+  constexpr int kMaxKbPerAccum = 64, kMaxKbLongK = 24, kMaxKbSmallOut = 8;
+  const int cap = (M * N * batch <= (1 << 21)) ? (g.nkb <= kMaxKbPerAccum ? kMaxKbSmallOut : 2 * kMaxKbSmallOut)
+                  : (splits > 1 && g.nkb > 4 * kMaxKbPerAccum) ? kMaxKbLongK : kMaxKbPerAccum;
   if ((g.nkb + splits - 1) / splits > cap) splits = (g.nkb + cap - 1) / cap;
   g.kb_per_split = (g.nkb + splits - 1) / splits;
   g.splits = (g.nkb + g.kb_per_split - 1) / g.kb_per_split;  // no empty split

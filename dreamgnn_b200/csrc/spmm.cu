@@ -224,6 +224,157 @@ spmm_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
   }
 }
 
+// ---- staged variant: gathered rows travel L2 -> shared memory by cp.async, not through registers ------------------------
+// The warp-per-row kernel above holds its in-flight loads in registers: 16 warps x 4 rows x 1376 B = 88 KB per SM at
+// d = 344, and measures ~10 TB/s of gather where the same access shape with twice the bytes in flight reaches 18-19 TB/s
+// (profiles/l2_peak.json): under load the L2 round trip is ~1.5 us, so throughput is (bytes in flight) / latency. Here
+// every lane copies ITS OWN 16-byte pieces of the next kRing - 1 rows into a per-warp ring with cp.async (LDGSTS: no
+// destination register) and reads them back after cp.async.wait_group -- shared memory as an extension of the register
+// file for loads in flight. A lane only ever reads bytes it copied itself, so no barrier of any kind is needed; one
+// commit group per row keeps the wait count a compile-time constant. fp32 features only.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NCHUNK, int kRing, bool kWeighted, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
+spmm_csr_stage_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, const float* __restrict__ vals,
+                      const float* __restrict__ src_scale, const float* __restrict__ dst_scale,
+                      const float* __restrict__ bias, const float* __restrict__ x, int64_t ldx, float* __restrict__ out,
+                      int64_t ldo, int64_t n_rows, int d, int n_slabs, int flags) {
+  static_assert((kRing & (kRing - 1)) == 0 && kRing <= 32, "ring size: power of two, at most one index batch");
+  constexpr int kSlabCols = 128 * NCHUNK;
+  extern __shared__ float4 ring_all[];                  // [8 warps][kRing][NCHUNK][32 lanes]
+  const int lane = lane_id(), wib = threadIdx.x >> 5;
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * 8 + wib;
+  const int64_t row = warp / n_slabs;
+  if (row >= n_rows) return;
+  const int slab = static_cast<int>(warp - row * n_slabs);
+  const int col0 = slab * kSlabCols + lane * 4;
+  float4* ring = ring_all + wib * (kRing * NCHUNK * 32);
+  const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring)) + lane * 16;
+  float acc[NCHUNK][4];
+  bool live[NCHUNK];
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    live[c] = col0 + c * 128 < d;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[c][v] = 0.f;
+  }
+  const int beg = indptr[row], n = indptr[row + 1] - beg;
+  auto load_batch = [&](int pos, int& jj, float& ww) {   // column (+ weight) of edge `pos` of the row, 0 past the end
+    jj = 0;
+    ww = 0.f;
+    if (pos < n) {
+      jj = ldg_i32_stream(indices + beg + pos);
+      if (kWeighted) ww = (vals ? vals[beg + pos] : 1.f) * (src_scale ? src_scale[jj] : 1.f);
+    }
+  };
+  auto issue = [&](int jj, int slot) {
+    const float* xr = x + static_cast<int64_t>(jj) * ldx + col0;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c)
+      if (live[c]) cp_async16(ring_s + (slot * NCHUNK + c) * 512, xr + c * 128);
+  };
+  int j, j_nx;
+  float w, w_nx;
+  load_batch(lane, j, w);
+  load_batch(32 + lane, j_nx, w_nx);
+#pragma unroll
+  for (int p = 0; p < kRing - 1; ++p) {                  // prologue: rows 0 .. kRing-2 on their way
+    const int jj = __shfl_sync(kFull, j, p);
+    if (p < n) issue(jj, p);
+    cp_async_commit();
+  }
+  for (int base = 0; base < n; base += 32) {
+    const int cnt = min(32, n - base);
+    for (int t = 0; t < cnt; ++t) {
+      const int pa = t + kRing - 1;                       // the row that enters the ring now (warp-uniform control flow)
+      const int jj = __shfl_sync(kFull, pa < 32 ? j : j_nx, pa & 31);
+      if (base + pa < n) issue(jj, (base + pa) & (kRing - 1));
+      cp_async_commit();
+      cp_async_wait<kRing - 1>();                         // row base + t has landed (this lane's pieces of it)
+      const float4* rs = ring + ((base + t) & (kRing - 1)) * NCHUNK * 32 + lane;
+      const float wt = kWeighted ? __shfl_sync(kFull, w, t) : 1.f;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c)
+        if (live[c]) {
+          const float4 b = rs[c * 32];
+          if (kWeighted) {
+            acc[c][0] = fmaf(wt, b.x, acc[c][0]); acc[c][1] = fmaf(wt, b.y, acc[c][1]);
+            acc[c][2] = fmaf(wt, b.z, acc[c][2]); acc[c][3] = fmaf(wt, b.w, acc[c][3]);
+          } else {
+            acc[c][0] += b.x; acc[c][1] += b.y; acc[c][2] += b.z; acc[c][3] += b.w;
+          }
+        }
+    }
+    j = j_nx;
+    w = w_nx;
+    load_batch(base + 64 + lane, j_nx, w_nx);
+  }
+  cp_async_wait<0>();
+  const float ds = dst_scale ? dst_scale[row] : 1.f;
+  float* orow = out + row * ldo;
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    if (!live[c]) continue;
+    const int col = col0 + c * 128;
+    float4 r = make_float4(acc[c][0] * ds, acc[c][1] * ds, acc[c][2] * ds, acc[c][3] * ds);
+    if (bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + col);
+      r.x += b.x; r.y += b.y; r.z += b.z; r.w += b.w;
+    }
+    float4* op = reinterpret_cast<float4*>(orow + col);
+    if (flags & DG_SPMM_ACCUMULATE) {
+      const float4 o = *op;
+      r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+    }
+    if (flags & DG_SPMM_RELU) {
+      r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+    }
+    *op = r;
+  }
+}
+
+static int spmm_stage_mode() {            // DG_SPMM_STAGE=1: staged instance for every fp32 launch it covers (experiment)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DG_SPMM_STAGE");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int NCHUNK, int kRing, int kMinBlocks>
+static int launch_spmm_stage(const int* indptr, const int* indices, const float* vals, const float* src_scale,
+                             const float* dst_scale, const float* bias, const float* x, int64_t ldx, float* out, int64_t ldo,
+                             int64_t n_rows, int d, int flags, cudaStream_t st) {
+  constexpr int kSlabCols = 128 * NCHUNK;
+  constexpr size_t kSmem = static_cast<size_t>(8) * kRing * NCHUNK * 512;
+  const int n_slabs = (d + kSlabCols - 1) / kSlabCols;
+  const int64_t blocks = (n_rows * n_slabs + 7) / 8;
+  if (blocks > 0x7fffffffLL) { set_error("spmm: grid too large"); return DG_ERR_INVALID_ARGUMENT; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    DG_CHECK_CUDA(cudaFuncSetAttribute(spmm_csr_stage_kernel<NCHUNK, kRing, true, kMinBlocks>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
+    DG_CHECK_CUDA(cudaFuncSetAttribute(spmm_csr_stage_kernel<NCHUNK, kRing, false, kMinBlocks>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
+    attr_set = true;
+  }
+  if (vals || src_scale)
+    spmm_csr_stage_kernel<NCHUNK, kRing, true, kMinBlocks><<<static_cast<unsigned>(blocks), 256, kSmem, st>>>(
+        indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
+  else
+    spmm_csr_stage_kernel<NCHUNK, kRing, false, kMinBlocks><<<static_cast<unsigned>(blocks), 256, kSmem, st>>>(
+        indptr, indices, vals, src_scale, dst_scale, bias, x, ldx, out, ldo, n_rows, d, n_slabs, flags);
+  DG_CHECK_LAUNCH("spmm_csr_stage");
+  return DG_OK;
+}
+
 // ---- row-split variant for graphs with FEW, LONG rows (the real datasets: ~700 rows of ~600 edges) ---------------
 // One CTA per (row, slab): its 8 warps take contiguous eighths of the row's 32-edge batches, accumulate exactly like
 // the warp-per-row kernel, and warp 0 adds the eight partial rows in warp order (fixed order: bit-reproducible) before
@@ -364,7 +515,7 @@ static int launch_spmm(const int* indptr, const int* indices, const float* vals,
   const int64_t blocks = (warps + 7) / 8;
   if (blocks > 0x7fffffffLL) { set_error("spmm: grid too large"); return DG_ERR_INVALID_ARGUMENT; }
   int pf = (flags & DG_SPMM_PREFETCH) ? spmm_prefetch_distance() : 0;
-  const int l1 = spmm_prefetch_l1();                                   // experiment: prefetch into L1 (any operand size)
+  const int l1 = (NCHUNK >= 3 && pf > 0) ? spmm_prefetch_l1() : 0;     // wide rows of out-of-L2 operands: prefetch into L1
   if (l1 > 0) pf = l1;
   if (pf * kUnroll > 32 - kUnroll) pf = (32 - kUnroll) / kUnroll;      // the window stays within one batch + the next
 #define DG_SPMM_LAUNCH(W, P)                                                                                   \
@@ -407,6 +558,16 @@ static int spmm_dispatch(const int* indptr, const int* indices, const float* val
     return DG_ERR_INVALID_ARGUMENT;
   }
   if (n_rows == 0) return DG_OK;
+  if (sizeof(typename L::Elem) == 4 && !(flags & DG_SPMM_ROWSPLIT)) {
+    const int mode = spmm_stage_mode();          // bit 0: wide rows (d > 256), bit 1: narrow rows (d <= 128)
+    const float* xf = reinterpret_cast<const float*>(x);
+    if ((mode & 1) && d > 256)
+      return launch_spmm_stage<3, 8, 2>(indptr, indices, vals, src_scale, dst_scale, bias, xf, ldx, out, ldo, n_rows,
+                                        static_cast<int>(d), flags, st);
+    if ((mode & 2) && d <= 128)
+      return launch_spmm_stage<1, 16, 3>(indptr, indices, vals, src_scale, dst_scale, bias, xf, ldx, out, ldo, n_rows,
+                                         static_cast<int>(d), flags, st);
+  }
   // pick the slab shape with the least lane waste: d <= 32V -> 1 chunk, <= 64V -> 2, else 3-chunk slabs
   const int per = 32 * L::kVec;
   const int dd = static_cast<int>(d);
