@@ -339,11 +339,21 @@ spmm_csr_stage_kernel(const int* __restrict__ indptr, const int* __restrict__ in
   }
 }
 
-static int spmm_stage_mode() {            // DG_SPMM_STAGE=1: staged instance for every fp32 launch it covers (experiment)
+// DG_SPMM_STAGE: bit 0 = staged instance for wide rows (d > 256; default on: measured -28 % on the d = 344 launches and
+// -20 % on d = 768 inside the syn20m step), bit 1 = also for narrow rows (d <= 128; measured +18 %: off).
+static int spmm_stage_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DG_SPMM_STAGE");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static int spmm_stage_ring() {            // DG_SPMM_RING=4|8|16: ring depth x resident CTAs (tuning; default 8 x 2)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DG_SPMM_RING");
+    v = e ? atoi(e) : 8;
   }
   return v;
 }
@@ -561,9 +571,15 @@ static int spmm_dispatch(const int* indptr, const int* indices, const float* val
   if (sizeof(typename L::Elem) == 4 && !(flags & DG_SPMM_ROWSPLIT)) {
     const int mode = spmm_stage_mode();          // bit 0: wide rows (d > 256), bit 1: narrow rows (d <= 128)
     const float* xf = reinterpret_cast<const float*>(x);
-    if ((mode & 1) && d > 256)
-      return launch_spmm_stage<3, 8, 2>(indptr, indices, vals, src_scale, dst_scale, bias, xf, ldx, out, ldo, n_rows,
-                                        static_cast<int>(d), flags, st);
+    if ((mode & 1) && d > 256) {
+#define DG_STAGE_ARGS indptr, indices, vals, src_scale, dst_scale, bias, xf, ldx, out, ldo, n_rows, static_cast<int>(d), flags, st
+      switch (spmm_stage_ring()) {
+        case 4: return launch_spmm_stage<3, 4, 4>(DG_STAGE_ARGS);
+        case 16: return launch_spmm_stage<3, 16, 1>(DG_STAGE_ARGS);
+        default: return launch_spmm_stage<3, 8, 2>(DG_STAGE_ARGS);
+      }
+#undef DG_STAGE_ARGS
+    }
     if ((mode & 2) && d <= 128)
       return launch_spmm_stage<1, 16, 3>(indptr, indices, vals, src_scale, dst_scale, bias, xf, ldx, out, ldo, n_rows,
                                          static_cast<int>(d), flags, st);

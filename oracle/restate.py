@@ -308,11 +308,13 @@ def attention(P, prefix, z, p=0.0, training=False):
     return (beta * z).sum(1), beta
 
 
-def mlp_decoder(P, prefix, src, dst, drug_feat, dis_feat, p=0.0, training=False):
-    """layers.py:360-379 `MLPDecoder.forward`: cat(h_drug[src], h_dis[dst]) -> 256-128-64-1 MLP."""
+def mlp_decoder(P, prefix, src, dst, drug_feat, dis_feat, p=0.0, training=False, masks=None):
+    """layers.py:360-379 `MLPDecoder.forward`: cat(h_drug[src], h_dis[dst]) -> 256-128-64-1 MLP. `masks` (checker only):
+    ReLU masks 'dec.z1' [E, 128] / 'dec.z2' [E, 64] of the implementation under test (see `_relu`)."""
+    m = masks or {}
     x = th.cat([drug_feat[_idx(src)], dis_feat[_idx(dst)]], 1)
-    x = F.dropout(F.relu(F.linear(x, P[prefix + 'lin1.weight'], P[prefix + 'lin1.bias'])), p, training)
-    x = F.dropout(F.relu(F.linear(x, P[prefix + 'lin2.weight'], P[prefix + 'lin2.bias'])), p, training)
+    x = F.dropout(_relu(F.linear(x, P[prefix + 'lin1.weight'], P[prefix + 'lin1.bias']), m.get('dec.z1')), p, training)
+    x = F.dropout(_relu(F.linear(x, P[prefix + 'lin2.weight'], P[prefix + 'lin2.bias']), m.get('dec.z2')), p, training)
     return F.linear(x, P[prefix + 'lin3.weight'], P[prefix + 'lin3.bias'])
 
 
@@ -330,7 +332,7 @@ def net_forward(P, enc_graph, dec_pairs, drug_graph, drug_sim_feat, drug_feat,
                                      drug_feature_graph, dis_feature_graph, dropout, training, relu_masks)[:2]
     drug_feats, _ = attention(P, 'attention.', th.stack([drug_out, drug_sim_out], 1), attention_dropout, training)
     dis_feats, _ = attention(P, 'attention.', th.stack([dis_out, dis_sim_out], 1), attention_dropout, training)
-    pred = mlp_decoder(P, 'decoder.', dec_pairs[0], dec_pairs[1], drug_feats, dis_feats, dropout, training)
+    pred = mlp_decoder(P, 'decoder.', dec_pairs[0], dec_pairs[1], drug_feats, dis_feats, dropout, training, relu_masks)
     return pred, drug_out, drug_sim_out, dis_out, dis_sim_out
 
 

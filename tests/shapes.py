@@ -127,14 +127,29 @@ import contextlib
 
 @contextlib.contextmanager
 def capture_relu_masks():
-    """Record the ReLU masks of the product path's FGCN route while a forward runs (dropout p = 0): the four gc1
-    activations (spmm + bias + ReLU in one kernel) and the two fusion activations, keyed as oracle/restate.py:fgcn expects.
+    """Record the ReLU masks of the product path while a forward runs (dropout p = 0): the four gc1 activations of the
+    FGCN route (spmm + bias + ReLU in one kernel), its two fusion activations, and the decoder's two hidden layers, keyed as
+    oracle/restate.py expects.
     The float64 oracle then differentiates through the SAME masks (restate._relu), which makes the gradient comparison
     well-posed: the handful of entries (out of ~10^6) whose pre-activation is within fp32 rounding of zero would otherwise
     each move a downstream gradient norm by ~1e-4."""
     from dreamgnn_b200 import ops
-    rec = {'spmm': [], 'act': []}
-    real_spmm, real_act = ops.spmm, ops.act_dropout
+    rec = {'spmm': [], 'act': [], 'dec': []}
+    real_spmm, real_act, real_dec = ops.spmm, ops.act_dropout, ops.decoder_mlp
+
+    def decoder_mlp(pd, ps, w2, b2, w3, b3, pairs, p=0.0, seed=0, training=False):
+        out = real_dec(pd, ps, w2, b2, w3, b3, pairs, p, seed, training)
+        with th.no_grad():
+            # hidden-1 mask: the kernel forms relu(pd[src] + ps[dst]) with one fp32 add, whose sign this reproduces exactly;
+            # hidden-2 mask: the forward's own saved state
+            z1 = th.empty((pairs.n_pairs, pd.shape[1]), dtype=th.bool)
+            for c0 in range(0, pairs.n_pairs, 1 << 20):
+                sl = slice(c0, c0 + (1 << 20))
+                z1[sl] = ((pd[pairs.src[sl].long()] + ps[pairs.dst[sl].long()]) > 0).cpu()
+            bits = ops.decoder_saved_mask(out).cpu() if out.requires_grad else None
+        z2 = None if bits is None else ((bits.unsqueeze(1) >> th.arange(64, dtype=th.int64)) & 1).bool()
+        rec['dec'].append((z1, z2))
+        return out
 
     def spmm(csr, x, src_scale=None, dst_scale=None, bias=None, relu=False, tag='spmm'):
         out = real_spmm(csr, x, src_scale, dst_scale, bias, relu, tag)
@@ -147,12 +162,14 @@ def capture_relu_masks():
         if act == 'relu':
             rec['act'].append((out.detach() > 0).cpu())
         return out
-    ops.spmm, ops.act_dropout = spmm, act_dropout
+    ops.spmm, ops.act_dropout, ops.decoder_mlp = spmm, act_dropout, decoder_mlp
     masks = {}
     try:
         yield masks
     finally:
-        ops.spmm, ops.act_dropout = real_spmm, real_act
+        ops.spmm, ops.act_dropout, ops.decoder_mlp = real_spmm, real_act, real_dec
+    if len(rec['dec']) == 1 and rec['dec'][0][1] is not None:
+        masks['dec.z1'], masks['dec.z2'] = rec['dec'][0]
     if len(rec['spmm']) == 4 and len(rec['act']) == 2:          # FGCN.forward order: drug (sim, feat), disease (sim, feat); fusions
         masks.update({'gc1.drug.sim': rec['spmm'][0], 'gc1.drug.feat': rec['spmm'][1], 'gc1.disease.sim': rec['spmm'][2],
                       'gc1.disease.feat': rec['spmm'][3], 'fusion.drug': rec['act'][0], 'fusion.disease': rec['act'][1]})
