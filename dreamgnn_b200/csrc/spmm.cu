@@ -349,11 +349,14 @@ static int spmm_stage_mode() {
   }
   return v;
 }
-static int spmm_stage_ring() {            // DG_SPMM_RING=4|8|16: ring depth x resident CTAs (tuning; default 8 x 2)
+// DG_SPMM_RING=4|8|16: ring depth (x 4 / 2 / 1 resident CTAs: ~190 KB of shared memory per SM either way). Measured inside
+// the syn20m step, d = 344 class / d = 768 class per step: 6.95 / 3.33 ms (4), 7.27 / 3.48 ms (8), 10.94 / 4.77 ms (16) --
+// more warps beat a deeper ring, so 4 x 4 is the default.
+static int spmm_stage_ring() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DG_SPMM_RING");
-    v = e ? atoi(e) : 8;
+    v = e ? atoi(e) : 4;
   }
   return v;
 }
@@ -574,9 +577,9 @@ static int spmm_dispatch(const int* indptr, const int* indices, const float* val
     if ((mode & 1) && d > 256) {
 #define DG_STAGE_ARGS indptr, indices, vals, src_scale, dst_scale, bias, xf, ldx, out, ldo, n_rows, static_cast<int>(d), flags, st
       switch (spmm_stage_ring()) {
-        case 4: return launch_spmm_stage<3, 4, 4>(DG_STAGE_ARGS);
+        case 8: return launch_spmm_stage<3, 8, 2>(DG_STAGE_ARGS);
         case 16: return launch_spmm_stage<3, 16, 1>(DG_STAGE_ARGS);
-        default: return launch_spmm_stage<3, 8, 2>(DG_STAGE_ARGS);
+        default: return launch_spmm_stage<3, 4, 4>(DG_STAGE_ARGS);
       }
 #undef DG_STAGE_ARGS
     }
