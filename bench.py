@@ -516,13 +516,17 @@ def measure_rows(ctx, workload, scale, steps, warmup, single_gpu_ms=None, check_
     gc.collect()
     th.cuda.empty_cache()
     model.train()
-    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5)
+    use_graph = os.environ.get('DG_ROWS_GRAPH', '1') != '0'
+    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5, capturable=use_graph)
     th.manual_seed(4321 + ctx.rank)                                    # per-rank dropout / noise streams
-    step = lambda: D.train_iteration_partitioned(model, opt, state)
+    eager_step = lambda: D.train_iteration_partitioned(model, opt, state)
+    step, launch = eager_step, 'eager launches (NCCL inside the step)'
+    if use_graph:
+        step = D.GraphedPartitionedIteration(model, opt, state, warmup=3)
+        launch = 'one CUDA-graph replay per rank and step (kernels and NCCL collectives captured together)'
     for _ in range(max(warmup, 3) + 2):
         step()
     ctx.barrier()
-    ops.PROFILE, D.PROFILE = [], []
     e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     ctx.barrier()
     e0.record()
@@ -531,8 +535,16 @@ def measure_rows(ctx, workload, scale, steps, warmup, single_gpu_ms=None, check_
     e1.record()
     ctx.barrier()
     ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    # per-launch SpMM events and per-collective events: from eager steps of the same iteration right after the timed region
+    # (graph replays carry no events)
+    log_steps = min(3, steps) if use_graph else steps
+    ops.PROFILE, D.PROFILE = [], []
+    for _ in range(log_steps):
+        eager_step()
+    th.cuda.synchronize()
     log, ops.PROFILE = ops.PROFILE, None
     clog, D.PROFILE = D.PROFILE, None
+    steps_timed, steps = steps, log_steps                               # the log-derived figures below are per logged step
     edges = th.tensor([sum(r[1] for r in log if r[0].startswith(('gcmc', 'fgcn'))) / steps], device=dev, dtype=th.float64)
     dist.all_reduce(edges)
     nccl_ms = ctx.max_over_ranks(sum(a.elapsed_time(b) for _, _, a, b in clog if a is not None) / steps)
@@ -549,20 +561,21 @@ def measure_rows(ctx, workload, scale, steps, warmup, single_gpu_ms=None, check_
     out = {'workload': '%s: %d drugs x %d diseases, %d scored pairs, ONE graph 1-D row-partitioned over %d GPUs'
                        % (workload, spec['n_drug'], spec['n_dis'], n_pairs, ctx.world),
            'ms_per_step': round(ms, 3), 'iters_per_sec': round(1e3 / ms, 4), 'GE/s': round(float(edges.item()) / (ms / 1e3) / 1e9, 4),
-           'scaling': 'strong', 'steps': steps,
+           'scaling': 'strong', 'steps': steps_timed,
            'strong_scaling_vs_1gpu': round(single_gpu_ms / ms, 3) if single_gpu_ms else None,
            'single_gpu_ms_per_step': round(single_gpu_ms, 3) if single_gpu_ms else None,
            'nccl_bytes_per_step': int(nccl_bytes), 'nccl_ms_per_step': round(nccl_ms, 3), 'nccl_share_of_step': round(nccl_ms / ms, 4),
            'collectives': by_kind,
            'nccl_timing': 'CUDA events on the compute stream around every blocking collective and around the stream-wait of '
                           'every deferred all-gather (rank-local sum, max over ranks) = the time the compute stream is held '
-                          'by communication',
+                          'by communication; taken from %d eager steps run after the timed region (includes the skew between '
+                          'ranks that an eager host loop adds)' % log_steps,
            'loss_matches_1gpu': {'loss_rows': loss_rows, 'loss_1gpu': loss_one, 'rel_diff': rel,
                                  'ok': None if rel is None else bool(rel <= 1e-5),
                                  'what': 'eval-mode forward + BCE + beta*common of the same weights on the same graph: N-rank '
                                          'partitioned path vs the single-GPU path on rank 0..N-1 (every rank holds the full graph once)'},
-           'launch': 'eager launches (NCCL inside the step)'}
-    del state, model, opt
+           'launch': launch}
+    del step, eager_step, state, model, opt
     gc.collect()
     th.cuda.empty_cache()
     return out
