@@ -297,7 +297,7 @@ class GraphConvolution(nn.Module):
     def support(self, input):
         return ops.project(input, self.weight.unsqueeze(0))[0]
 
-    def aggregate(self, support, adj, relu=False):
+    def aggregate(self, support, adj, relu=False, gathered=None):
         d = support.shape[1]
         bias = self.bias
         if d % 4:
@@ -305,7 +305,8 @@ class GraphConvolution(nn.Module):
             bias = _pad_cols(bias, 4) if bias is not None else None
         if hasattr(adj, 'partition'):                            # owned rows of a row-partitioned kNN graph
             from . import dist as _dist
-            out = ops.spmm(adj.csr, _dist.all_gather_rows(support), bias=bias, relu=relu, tag='fgcn')
+            full = gathered if gathered is not None else _dist.all_gather_rows(support)
+            out = ops.spmm(adj.csr, full, bias=bias, relu=relu, tag='fgcn')
         else:
             out = ops.spmm(adjacency_csr(adj), support, bias=bias, relu=relu, tag='fgcn')
         return out[:, :d] if out.shape[1] != d else out
@@ -328,8 +329,8 @@ class GCN(nn.Module):
         self.gc2 = GraphConvolution(nhid, nhid2)
         self.dropout = dropout
 
-    def _tail(self, support1, adj):
-        x = self.gc1.aggregate(support1, adj, relu=True)          # spmm + bias + ReLU in one kernel
+    def _tail(self, support1, adj, gathered=None):
+        x = self.gc1.aggregate(support1, adj, relu=True, gathered=gathered)      # spmm + bias + ReLU in one kernel
         x = ops.act_dropout(x, None, p=self.dropout, training=self.training)
         return self.gc2(x, adj)
 
@@ -340,7 +341,13 @@ class GCN(nn.Module):
         """Same layer on several graphs over the same input: x @ W1 is computed once (the reference
         recomputes it per graph, layers.py:263-270)."""
         s1 = self.gc1.support(x)
-        return [self._tail(s1, adj) for adj in adjs]
+        gathered = None
+        if adjs and hasattr(adjs[0], 'partition') and s1.shape[1] % 4 == 0:
+            # row-partitioned graphs: the [n_loc, nhid1] support is all-gathered ONCE for both graphs (its gradient comes
+            # back through one reduce-scatter of the two consumers' summed gradients)
+            from . import dist as _dist
+            gathered = _dist.all_gather_rows(s1)
+        return [self._tail(s1, adj, gathered) for adj in adjs]
 
 
 class FGCN(nn.Module):
@@ -373,10 +380,14 @@ class FGCN(nn.Module):
         if self.training and self.dropout > 0:
             # keep the reference's dropout draw order: drug(sim), disease(sim), drug(feat), disease(feat)
             s_d, s_s = self.FGCN_drug.gc1.support(drug_sim_feat), self.FGCN_disease.gc1.support(disease_sim_feat)
-            emb1_sim = self.FGCN_drug._tail(s_d, drug_graph)
-            emb2_sim = self.FGCN_disease._tail(s_s, dis_graph)
-            emb1_feat = self.FGCN_drug._tail(s_d, drug_feature_graph)
-            emb2_feat = self.FGCN_disease._tail(s_s, disease_feature_graph)
+            g_d = g_s = None
+            if hasattr(drug_graph, 'partition') and s_d.shape[1] % 4 == 0:      # row-partitioned: one all-gather per node type
+                from . import dist as _dist
+                g_d, g_s = _dist.all_gather_rows(s_d), _dist.all_gather_rows(s_s)
+            emb1_sim = self.FGCN_drug._tail(s_d, drug_graph, g_d)
+            emb2_sim = self.FGCN_disease._tail(s_s, dis_graph, g_s)
+            emb1_feat = self.FGCN_drug._tail(s_d, drug_feature_graph, g_d)
+            emb2_feat = self.FGCN_disease._tail(s_s, disease_feature_graph, g_s)
         else:
             emb1_sim, emb1_feat = self.FGCN_drug.forward_shared(drug_sim_feat, [drug_graph, drug_feature_graph])
             emb2_sim, emb2_feat = self.FGCN_disease.forward_shared(disease_sim_feat, [dis_graph, disease_feature_graph])
