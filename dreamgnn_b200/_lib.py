@@ -37,7 +37,7 @@ _SIGNATURES = {
     'dg_decoder_fwd_f32': (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, c_float, c_uint64, _P, _P, _P, _P]),
     'dg_decoder_bwd_workspace_bytes': (c_size_t, [c_int64]),
     'dg_decoder_bwd_f32': (c_int, [_P, _P, _P, c_int64, _P, _P, _P, _P, c_float, c_uint64, _P, _P, _P, _P, _P, _P, _P, _P,
-                                   _P, c_size_t, _P]),
+                                   _P, _P, _P, c_size_t, _P]),
     'dg_gemm_nt_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
     'dg_gemm_nt_f32': (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, c_int64,
                                c_int64, _P, c_int, _P, c_size_t, _P]),

@@ -352,9 +352,12 @@ size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs) {
 int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_pairs, const float* pd, const float* ps,
                        const float* w2, const float* w3, float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* z2,
                        const float* dout, float* dz1, float* dw2, float* db2, float* dw3, float* db3,
-                       void* workspace, size_t workspace_bytes, dg_stream_t stream) {
+                       const int32_t* pair_slot, float* slot_rows, void* workspace, size_t workspace_bytes, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(n_pairs >= 0, "n_pairs < 0");
+  DG_REQUIRE((pair_slot == nullptr) == (slot_rows == nullptr), "pair_slot and slot_rows go together");
+  DG_REQUIRE(pair_slot == nullptr || !use_simt_decoder(), "the fused source-node segment sum needs the tensor-core kernel");
+  DG_REQUIRE((reinterpret_cast<uintptr_t>(pair_slot) & 15) == 0, "pair_slot must be 16-byte aligned");
   DG_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p must be in [0,1)");
   Workspace w(workspace, workspace_bytes);
   float* partials = w.take<float>(static_cast<size_t>(kNumSM) * 2 * kPartial);
@@ -362,7 +365,7 @@ int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, const int32_t* pe
   int grid = 0;
   if (!use_simt_decoder()) {
     DG_PROPAGATE(launch_decoder_bwd_tc(src, dst, perm, n_pairs, pd, ps, w2, w3, make_drop(dropout_p, seed, seed_dev), z2, dout, dz1,
-                                       partials, &grid, as_stream(stream)));
+                                       partials, &grid, pair_slot, slot_rows, as_stream(stream)));
   } else {
     static bool attr_set = false;
     if (!attr_set) {

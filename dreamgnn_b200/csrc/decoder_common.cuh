@@ -39,6 +39,6 @@ int launch_decoder_fwd_tc(const int* src, const int* dst, const int* perm, int64
                           cudaStream_t st);
 int launch_decoder_bwd_tc(const int* src, const int* dst, const int* perm, int64_t n_pairs, const float* pd, const float* ps, const float* w2,
                           const float* w3, DropCfg drop, const float* z2, const float* dout, float* dz1, float* partials,
-                          int* n_ctas, cudaStream_t st);
+                          int* n_ctas, const int* pair_slot, float* slot_rows, cudaStream_t st);
 
 }  // namespace dg

@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, const int* __restrict__ perm, int64_t n_pairs,
                       const float* __restrict__ pd, const float* __restrict__ ps, const float* __restrict__ w2,
                       const float* __restrict__ w3, DropCfg drop, const float* __restrict__ z2,
-                      const float* __restrict__ dout, float* __restrict__ dz1, float* __restrict__ partials, int flush_tiles) {
+                      const float* __restrict__ dout, float* __restrict__ dz1, float* __restrict__ partials, int flush_tiles,
+                      const int* __restrict__ pair_slot, float* __restrict__ slot_rows) {
   if (drop.seed_dev) drop.seed = *drop.seed_dev;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzle atoms, kept as an offset from the __shared__ array so that the compiler
@@ -474,13 +475,46 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
       tmem_ld_wait();
       const float sc = drop.scale;
       const uint8_t* zrow = Z_hi + q * kBBlk + (lane & 7) * 4;             // unit 32q + lane: 32-byte chunk lane >> 3
+      // Segment sums by source node, fused: `pair_slot[e]` numbers the runs of equal source inside aligned 16-pair groups
+      // (the pairs are walked in an order that is sorted by source inside each label class, so a run is usually the whole
+      // group). This thread owns unit 32q + lane of exactly one group, so it sums its 16 values run by run in pair order
+      // and writes one row element per run into slot_rows [n_slots, 128]: no other thread touches that (slot, unit), no
+      // atomics, fixed order. The host adds the few slots of each source node in slot order (a 1.5 M-row segment sum
+      // instead of re-reading the 10 GB dz1).
+      int sl[16];
+      if (pair_slot) {
+        const int64_t e0 = base + g * 16;
+        if (e0 + 16 <= n_pairs) {
+          const int4* ps4 = reinterpret_cast<const int4*>(pair_slot + e0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int4 t4 = __ldg(ps4 + i);
+            sl[4 * i] = t4.x; sl[4 * i + 1] = t4.y; sl[4 * i + 2] = t4.z; sl[4 * i + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sl[j] = (e0 + j < n_pairs) ? __ldg(pair_slot + e0 + j) : -1;
+        }
+      }
+      int cur = -1;
+      float run = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int p = g * 16 + j;
         const int64_t e = base + p;
         const float z = *reinterpret_cast<const float*>(zrow + p * 128 + (((lane >> 3) ^ (p & 3)) << 5));
-        if (e < n_pairs) __stcs(dz1 + e * H1 + q * 32 + lane, z > 0.f ? __uint_as_float(v[j]) * sc : 0.f);
+        const float val = z > 0.f ? __uint_as_float(v[j]) * sc : 0.f;
+        if (e < n_pairs) __stcs(dz1 + e * H1 + q * 32 + lane, val);
+        if (pair_slot) {
+          if (sl[j] != cur) {                                              // warp-uniform: every lane sees the same pairs
+            if (cur >= 0) slot_rows[static_cast<int64_t>(cur) * H1 + q * 32 + lane] = run;
+            cur = sl[j];
+            run = 0.f;
+          }
+          run += val;
+        }
       }
+      if (pair_slot && cur >= 0) slot_rows[static_cast<int64_t>(cur) * H1 + q * 32 + lane] = run;
     }
     mbar_wait(bar2, it & 1);                             // z1 / dz2 tiles free again
     tc_fence_after();
@@ -558,7 +592,7 @@ int launch_decoder_fwd_tc(const int* src, const int* dst, const int* perm, int64
 
 int launch_decoder_bwd_tc(const int* src, const int* dst, const int* perm, int64_t n_pairs, const float* pd, const float* ps, const float* w2,
                           const float* w3, DropCfg drop, const float* z2, const float* dout, float* dz1, float* partials,
-                          int* n_ctas, cudaStream_t st) {
+                          int* n_ctas, const int* pair_slot, float* slot_rows, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     DG_CHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBwdTcSmem)));
@@ -568,7 +602,7 @@ int launch_decoder_bwd_tc(const int* src, const int* dst, const int* perm, int64
   const int grid = tc_grid(n_tiles);
   const char* ft = getenv("DG_DEC_FLUSH");           // tuning switch
   decoder_bwd_tc_kernel<<<grid, kTcThreads, kBwdTcSmem, st>>>(src, dst, perm, n_pairs, pd, ps, w2, w3, drop, z2, dout, dz1, partials,
-                                                              ft ? atoi(ft) : kFlushTiles);
+                                                              ft ? atoi(ft) : kFlushTiles, pair_slot, slot_rows);
   DG_CHECK_LAUNCH("decoder_bwd_tc");
   *n_ctas = grid;
   return DG_OK;

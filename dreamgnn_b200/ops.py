@@ -567,6 +567,7 @@ class PairGraph:
         self.src, self.dst = _i32(src, 'src'), _i32(dst, 'dst')
         self.n_src, self.n_dst = int(n_src), int(n_dst)
         self._by_src = self._by_dst = self._order = None
+        self._slots = {}
 
     @property
     def n_pairs(self):
@@ -586,6 +587,26 @@ class PairGraph:
         if self._by_dst is None:
             self._by_dst = self._segments(self.dst, self.n_dst)
         return self._by_dst
+
+    SLOT_GROUP = 16                       # pairs per epilogue thread of the backward kernel (decoder_tc.cu)
+
+    def source_slots(self, by_drug=False):
+        """Plan of the source-node segment sum fused into the backward's epilogue: (pair_slot int32 [E], n_slots,
+        CSR over slots by source node). In processing order, a new slot starts at every multiple of 16 pairs and wherever
+        the source node changes -- label order is sorted by drug inside each label class, so almost every aligned group of
+        16 pairs is one slot. Built once per pair graph (one host read of the slot count)."""
+        key = bool(by_drug)
+        if key not in self._slots:
+            src = self.processing_order()[1] if by_drug else self.src
+            e = self.n_pairs
+            pos = th.arange(e, device=src.device)
+            new = (pos % self.SLOT_GROUP) == 0
+            new[1:] |= src[1:] != src[:-1]
+            slot = (th.cumsum(new.to(th.int32), 0, dtype=th.int32) - 1).contiguous()
+            n_slots = int(slot[-1]) + 1
+            seg = CSR.from_coo(src[new], th.arange(n_slots, dtype=I32, device=src.device), self.n_src, n_slots)
+            self._slots[key] = (slot, n_slots, seg)
+        return self._slots[key]
 
     def processing_order(self):
         """(perm, src_p, dst_p, seg_src, seg_dst): perm[i] = label position of the i-th processed pair (pairs
@@ -648,14 +669,29 @@ class DecoderFunction(th.autograd.Function):
         dw3 = th.empty((1, DEC_H2), dtype=th.float32, device=dev)
         db3 = th.empty(1, dtype=th.float32, device=dev)
         ws = L.workspace(lib.dg_decoder_bwd_workspace_bytes(e), dev)
-        perm, src_p, dst_p, seg_src, seg_dst = pairs.processing_order() if ctx.by_drug else (None, pairs.src, pairs.dst,
-                                                                                             pairs.by_src(), pairs.by_dst())
+        if ctx.by_drug:
+            perm, src_p, dst_p, seg_src, seg_dst = pairs.processing_order()
+        else:
+            perm, src_p, dst_p, seg_dst = None, pairs.src, pairs.dst, pairs.by_dst()
+        # the segment sum by source node rides in the kernel's epilogue (one partial row per run of equal source inside
+        # aligned 16-pair groups) unless the SIMT kernels or DG_DECODER_SEG=spmm are selected
+        fuse = (e > 0 and ctx.needs_input_grad[0] and os.environ.get('DG_DECODER', 'tc') != 'simt'
+                and os.environ.get('DG_DECODER_SEG', 'fused') == 'fused')
+        pair_slot = slot_rows = seg_slots = None
+        if fuse:
+            pair_slot, n_slots, seg_slots = pairs.source_slots(ctx.by_drug)
+            slot_rows = th.empty((n_slots, DEC_H1), dtype=th.float32, device=dev)
         L.check(lib.dg_decoder_bwd_f32(L.ptr(src_p), L.ptr(dst_p), L.ptr(perm), e, L.ptr(pd), L.ptr(ps), L.ptr(w2),
                                        L.ptr(w3), ctx.p, ctx.seed, L.ptr(ctx.seed_dev), L.ptr(z2), L.ptr(dout, th.float32, 'dout'),
-                                       L.ptr(dz1), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3), L.ptr(ws),
-                                       ws.numel(), L.stream()), 'decoder_bwd')
-        # scatter of dz1 (processing order) into node gradients = two segment sums in fixed order (no atomics)
-        dpd = _spmm_raw(seg_src, dz1, tag='decoder.seg') if ctx.needs_input_grad[0] else None
+                                       L.ptr(dz1), L.ptr(dw2), L.ptr(db2), L.ptr(dw3), L.ptr(db3), L.ptr(pair_slot),
+                                       L.ptr(slot_rows), L.ptr(ws), ws.numel(), L.stream()), 'decoder_bwd')
+        # scatter of dz1 (processing order) into node gradients = segment sums in fixed order (no atomics)
+        if fuse:
+            dpd = _spmm_raw(seg_slots, slot_rows, tag='decoder.slots')
+        elif ctx.needs_input_grad[0]:
+            dpd = _spmm_raw(pairs.processing_order()[3] if ctx.by_drug else pairs.by_src(), dz1, tag='decoder.seg')
+        else:
+            dpd = None
         dps = _spmm_raw(seg_dst, dz1, tag='decoder.seg') if ctx.needs_input_grad[1] else None
         return dpd, dps, dw2, db2, dw3, db3, None, None, None, None
 

@@ -165,13 +165,18 @@ DG_API int dg_decoder_fwd_f32(const int32_t* src, const int32_t* dst, const int3
  * dz1 [n_pairs,128] = d loss / d (pd[src]+ps[dst]) and the parameter gradients dw2 [64,128], db2 [64],
  * dw3 [64], db3 [1] (per-CTA partials summed in CTA order). d pd / d ps are then two deterministic
  * segment sums of dz1 over the decoder graph's CSR / CSC (dg_spmm_csr_f32 with indices = edge ids)
- * -- no atomics. */
+ * -- no atomics. Optionally the sum by SOURCE node is fused into the kernel's epilogue: pair_slot [n_pairs]
+ * (16-byte aligned) numbers, in processing order, the runs of equal source inside aligned 16-pair groups (a new
+ * slot starts at every multiple of 16 and wherever the source changes); the kernel writes slot_rows
+ * [n_slots, 128] = sum of dz1 over each run, and the caller adds the slots of each node (a segment sum over
+ * n_slots ~ n_pairs / 16 rows instead of n_pairs). Both NULL = off. Tensor-core kernel only. */
 DG_API size_t dg_decoder_bwd_workspace_bytes(int64_t n_pairs);
 DG_API int dg_decoder_bwd_f32(const int32_t* src, const int32_t* dst, const int32_t* perm, int64_t n_pairs,
                        const float* pd, const float* ps, const float* w2, const float* w3,
                        float dropout_p, uint64_t seed, const uint64_t* seed_dev, const float* z2,
                        const float* dout,
                        float* dz1, float* dw2, float* db2, float* dw3, float* db3,
+                       const int32_t* pair_slot, float* slot_rows,
                        void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
 /* ---- dense projections on the tcgen05 tensor cores -------------------------------------------------

@@ -237,6 +237,35 @@ def test_decoder_forward_backward(dev, n_pairs, impl, order, monkeypatch):
     assert th.equal(hdg.grad, g1)
 
 
+@pytest.mark.parametrize('n_pairs,sorted_src', [(5000, True), (5000, False), (17, True), (40001, True)])
+def test_decoder_fused_source_segment_sum(dev, n_pairs, sorted_src, monkeypatch):
+    """The segment sum by source node fused into the backward's epilogue (one partial row per run of equal source inside
+    aligned 16-pair groups, then a sum over slots) against the plain segment-sum SpMM over dz1: same gradient to fp32
+    reassociation, and the slot plan has one slot per 16 pairs plus one per extra run."""
+    o = ops()
+    gen = th.Generator().manual_seed(n_pairs)
+    rng = np.random.default_rng(n_pairs)
+    n_d, n_s = 41, 33
+    src, dst = rng.integers(0, n_d, n_pairs), rng.integers(0, n_s, n_pairs)
+    if sorted_src:
+        src = np.sort(src)
+    pairs = o.PairGraph(th.tensor(src, device=dev), th.tensor(dst, device=dev), n_d, n_s)
+    slot, n_slots, seg = pairs.source_slots()
+    runs = 1 + int(((np.arange(1, n_pairs) % 16 == 0) | (src[1:] != src[:-1])).sum())
+    assert n_slots == runs and slot.numel() == n_pairs and int(slot[-1]) == n_slots - 1
+    mk = lambda *sh: (th.randn(*sh, generator=gen) * 0.3).to(dev)
+    ps, w2, b2, w3, b3 = mk(n_s, 128), mk(64, 128), mk(64), mk(1, 64), mk(1)
+    pd0 = mk(n_d, 128)
+    gout = th.randn(n_pairs, 1, generator=gen).to(dev)
+    grads = {}
+    for mode in ('fused', 'spmm'):
+        monkeypatch.setenv('DG_DECODER_SEG', mode)
+        pd = pd0.clone().requires_grad_(True)
+        o.decoder_mlp(pd, ps, w2, b2, w3, b3, pairs, training=True).backward(gout)
+        grads[mode] = pd.grad.clone()
+    assert H.rel_err(grads['fused'].cpu(), grads['spmm'].cpu()) <= 2e-6
+
+
 @pytest.mark.parametrize('order', ['label', 'by-drug'])
 def test_decoder_dropout_is_consistent_between_forward_and_backward(dev, order, monkeypatch):
     """Training mode: the backward regenerates the forward's masks. Checked as a directional derivative of
