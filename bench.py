@@ -400,7 +400,7 @@ def roofline_block(res):
     log, log_steps = res['log'], res['log_steps']
     classes = {}
     for tag, nnz, nr, nc, d, el, valued, a, b in log:
-        key = (tag.split('.')[0], d, el)
+        key = (tag.replace('.bwd', '').replace('.', '_'), d, el)      # gcmc | fgcn | decoder_seg | decoder_slots
         c = classes.setdefault(key, dict(ms=0.0, gather=0.0, bmin=0.0, n=0, nnz=0))
         c['ms'] += a.elapsed_time(b)
         c['gather'] += spmm_gather_bytes(nnz, nr, nc, d, el, valued)

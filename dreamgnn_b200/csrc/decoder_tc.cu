@@ -496,7 +496,6 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
           for (int j = 0; j < 16; ++j) sl[j] = (e0 + j < n_pairs) ? __ldg(pair_slot + e0 + j) : -1;
         }
       }
-      int cur = -1;
       float run = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -505,16 +504,30 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
         const float z = *reinterpret_cast<const float*>(zrow + p * 128 + (((lane >> 3) ^ (p & 3)) << 5));
         const float val = z > 0.f ? __uint_as_float(v[j]) * sc : 0.f;
         if (e < n_pairs) __stcs(dz1 + e * H1 + q * 32 + lane, val);
-        if (pair_slot) {
-          if (sl[j] != cur) {                                              // warp-uniform: every lane sees the same pairs
-            if (cur >= 0) slot_rows[static_cast<int64_t>(cur) * H1 + q * 32 + lane] = run;
-            cur = sl[j];
-            run = 0.f;
+        run += val;                                                        // pairs past the end contribute exact zeros
+      }
+      if (pair_slot) {
+        float* srow = slot_rows + q * 32 + lane;
+        if (sl[0] == sl[15]) {                                             // the whole group is one run (~9 groups in 10)
+          if (sl[0] >= 0) srow[static_cast<int64_t>(sl[0]) * H1] = run;
+        } else {                                                           // run boundaries inside the group: walk it again
+          int cur = -1;
+          run = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int p = g * 16 + j;
+            const float z = *reinterpret_cast<const float*>(zrow + p * 128 + (((lane >> 3) ^ (p & 3)) << 5));
+            const float val = z > 0.f ? __uint_as_float(v[j]) * sc : 0.f;
+            if (sl[j] != cur) {                                            // warp-uniform: every lane sees the same pairs
+              if (cur >= 0) srow[static_cast<int64_t>(cur) * H1] = run;
+              cur = sl[j];
+              run = 0.f;
+            }
+            run += val;
           }
-          run += val;
+          if (cur >= 0) srow[static_cast<int64_t>(cur) * H1] = run;
         }
       }
-      if (pair_slot && cur >= 0) slot_rows[static_cast<int64_t>(cur) * H1 + q * 32 + lane] = run;
     }
     mbar_wait(bar2, it & 1);                             // z1 / dz2 tiles free again
     tc_fence_after();

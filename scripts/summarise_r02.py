@@ -61,8 +61,8 @@ if os.path.isfile(path):
     for r in spmm:
         wide = 'LoadF32, 3' in r['name'] or 'stage_kernel<3' in r['name']     # d = 344 / 768: the staged instance since round 2
         seg = 'LoadF32, 1, 8, 0' in r['name']            # unweighted d=128: the decoder's segment sums
-        if seg:
-            cls['decoder_d128'].append(r)
+        if seg:                                              # unweighted d=128: the decoder's node-gradient sums
+            cls['decoder_seg_d128' if r['ms'] > 0.8 else 'decoder_slots_d128'].append(r)
         elif wide and r['ms'] > 1.0:
             cls['gcmc_d344'].append(r)
         elif wide:
