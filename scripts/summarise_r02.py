@@ -144,8 +144,12 @@ if os.path.isfile(path):
     open(os.path.join(P, 'r02_launches_syn20m_step.md'), 'w').write('\n'.join(md) + '\n')
     shutil.copy(path, os.path.join(P, 'r02_launches_syn20m_step.csv'))
 for src, dst in (('r02_bench_full.json', 'r02_bench_syn20m_full_line.json'), ('r02_bench_2gpu.json', 'r02_bench_syn20m_2gpu.json'),
-                 ('r02_bench_reference.json', 'r02_bench_reference_arm.json'), ('l2_peak.json', 'l2_peak.json')):
+                 ('r02_bench_reference.json', 'r02_bench_reference_arm.json')):
     if os.path.isfile(os.path.join(G, src)):
         lines = [ln for ln in open(os.path.join(G, src)).read().splitlines() if ln.startswith('{')]
         if lines:
             open(os.path.join(P, dst), 'w').write(lines[-1] + '\n')        # the JSON line only (NCCL banner dropped)
+
+# the microbenchmark file is indented JSON: copied whole
+if os.path.isfile(os.path.join(G, 'l2_peak.json')):
+    json.dump(json.load(open(os.path.join(G, 'l2_peak.json'))), open(os.path.join(P, 'l2_peak.json'), 'w'), indent=1)
