@@ -137,8 +137,11 @@ def spmm_compulsory_bytes(nnz, n_rows, n_cols, d, elem, valued):
 def _json_file(*parts):
     p = os.path.join(REPO, *parts)
     if os.path.isfile(p):
-        with open(p) as fh:
-            return json.load(fh)
+        try:
+            with open(p) as fh:
+                return json.load(fh)
+        except ValueError:                       # a damaged side file must never take the bench line down
+            return None
     return None
 
 

@@ -163,3 +163,12 @@ def test_edge_sampler_choice_on_cpu(monkeypatch):
     monkeypatch.setenv('DG_EDGE_SAMPLER', 'select')
     assert isinstance(_randperm(10, 'cpu'), th.Tensor)        # the select sampler is a CUDA kernel: CPU graphs keep randperm
     assert num_keep_edges(467641, 0.1) == int(467641 * 0.9) and num_keep_edges(1, 0.99) == 1
+
+
+def test_bench_side_files_parse():
+    """profiles/roofline_traffic.json and profiles/l2_peak.json feed bench.py's roofline block."""
+    import json
+    tr = json.load(open(os.path.join(REPO, 'profiles', 'roofline_traffic.json')))
+    assert 'kernel_digest' in tr and all(isinstance(tr[k], int) for k in tr if k.endswith(('d128', 'd344', 'd768')))
+    l2 = json.load(open(os.path.join(REPO, 'profiles', 'l2_peak.json')))
+    assert l2['l2_gather_d344']['GBps'] > 1000 and l2['hbm_seq']['GBps'] > 1000
