@@ -454,6 +454,9 @@ def roofline_block(res):
         tot['ms'] += v['ms']; tot['bmin'] += v['bmin']; tot['gather'] += v['gather']; tot['n'] += v['n']
         if per_launch_traffic:
             tot['dram'] += per_launch_traffic * v['n']
+        elif tr is not None:                    # a class the capture does not list: counted at its compulsory bytes (a floor)
+            tot['dram'] += v['bmin']
+            tot.setdefault('floor', []).append('%s_d%d' % (tag, d))
         else:
             tot['known'] = False
     secs = tot['ms'] / 1e3
@@ -461,6 +464,8 @@ def roofline_block(res):
     if tot['known']:
         achieved, basis = tot['dram'] / secs / 1e9, ('DRAM traffic of the launches (ncu dram__bytes_read + dram__bytes_write per '
                                                       'launch of each class) / their CUDA-event durations')
+        if tot.get('floor'):
+            basis += '; classes missing from the capture counted at their compulsory bytes: %s' % ', '.join(tot['floor'])
         traffic = int(tot['dram'] / tot['n'])
     else:
         achieved, basis, traffic = bmin_gbps, 'compulsory bytes B_min (SURVEY 8d; every operand once) / CUDA-event durations', None
