@@ -97,7 +97,28 @@ template <int U>
 struct GatherRegs {
   float4 a[U], b[U];
   int s, d;                // lane u < U: endpoints of pair u of the tile after the one in a / b (the index loads run two
-};                         // tiles ahead, so the row loads never wait on them); -1 past the end
+                           // tiles ahead, so the row loads never wait on them); -1 past the end
+  uint32_t keep;           // dropout keep decisions of the tile in a / b: bit 4u + q = unit 4*lane + q of pair u survives
+};
+
+// The keep decisions depend on (seed, pair, unit) only, not on loaded data: they are hashed for the NEXT tile right before
+// the wait for the current tile's MMAs -- ~36 integer instructions per pair and lane that would otherwise sit on the
+// critical path in front of the operand commit run in the shadow of the tensor core (all 16 warps idle-spin there).
+template <int U>
+__device__ __forceinline__ uint32_t gather_keep_bits(int64_t base, const DropCfg& drop) {
+  static_assert(U * 4 <= 32, "one mask word per tile and lane");
+  uint32_t m = 0;
+  if (drop.thresh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const DropBits bits = dropout_bits(drop.seed, static_cast<uint32_t>(base + warp * U + u), lane);      // units 4*lane .. +3
+#pragma unroll
+      for (int q = 0; q < 4; ++q) m |= static_cast<uint32_t>(dropout_keep16(bits, q, drop.thresh)) << (u * 4 + q);
+    }
+  }
+  return m;
+}
 
 template <int U>
 __device__ __forceinline__ void gather_issue_idx(const int* __restrict__ src, const int* __restrict__ dst, int64_t base,
@@ -135,12 +156,10 @@ __device__ __forceinline__ void gather_commit(const GatherRegs<U>& r, int64_t ba
   for (int u = 0; u < U; ++u) {
     const int p = warp * U + u;
     float z[4] = {r.a[u].x + r.b[u].x, r.a[u].y + r.b[u].y, r.a[u].z + r.b[u].z, r.a[u].w + r.b[u].w};
-    DropBits bits;
-    if (drop.thresh) bits = dropout_bits(drop.seed, static_cast<uint32_t>(base + p), lane);      // units 4*lane .. +3
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float v = fmaxf(z[q], 0.f);
-      if (drop.thresh) v = dropout_keep16(bits, q, drop.thresh) ? v * drop.scale : 0.f;
+      if (drop.thresh) v = ((r.keep >> (u * 4 + q)) & 1u) ? v * drop.scale : 0.f;
       z[q] = v;
     }
     const uint32_t off = blk_off + (kMnMajor ? mn32_off(p, lane & 7) : sw128_off(p, lane & 7));
@@ -215,6 +234,7 @@ decoder_fwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
   gather_issue_idx<U>(src, dst, tile * kFT, n_pairs, regs);               // (past-the-end tiles load nothing)
   gather_issue_rows<U>(pd, ps, regs);
   gather_issue_idx<U>(src, dst, (tile + gridDim.x) * kFT, n_pairs, regs);
+  regs.keep = gather_keep_bits<U>(tile * kFT, drop);
   for (; tile < n_tiles; tile += gridDim.x) {
     const int64_t base = tile * kFT;
     gather_commit<kFT, U, false>(regs, base, drop, A_hi, A_lo);
@@ -238,6 +258,17 @@ decoder_fwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
     // next tile's rows (and the endpoints of the one after): in flight while the tensor core and the epilogue work
     gather_issue_rows<U>(pd, ps, regs);
     gather_issue_idx<U>(src, dst, (tile + 2 * static_cast<int64_t>(gridDim.x)) * kFT, n_pairs, regs);
+    // dropout decisions in the shadow of the MMAs: the next tile's hidden-1 units and this tile's hidden-2 units (epilogue)
+    regs.keep = gather_keep_bits<U>((tile + gridDim.x) * kFT, drop);
+    uint32_t keep2 = 0;                                   // bit 4c + r = unit j0 + 4c + r of pair base + 32q + lane survives
+    if (drop.thresh && q * 32 < kFT) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const DropBits bits = dropout_bits(drop.seed, static_cast<uint32_t>(base + q * 32 + lane), H1 / 4 + (j0 >> 2) + c);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) keep2 |= static_cast<uint32_t>(dropout_keep16(bits, r, drop.thresh)) << (c * 4 + r);
+      }
+    }
     mbar_wait(bar_a, phase);
     phase ^= 1;
     tc_fence_after();
@@ -274,12 +305,10 @@ decoder_fwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c = c2 * 2 + h;
-          DropBits bits;
-          if (drop.thresh) bits = dropout_bits(drop.seed, static_cast<uint32_t>(e), H1 / 4 + (j0 >> 2) + c);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             float x = fmaxf((acc[c * 4 + r] + __uint_as_float(v[c * 4 + r])) + b2s[j0 + c * 4 + r], 0.f);
-            if (drop.thresh) x = dropout_keep16(bits, r, drop.thresh) ? x * drop.scale : 0.f;
+            if (drop.thresh) x = ((keep2 >> (c * 4 + r)) & 1u) ? x * drop.scale : 0.f;
             z2[h * 4 + r] = x;
           }
         }
@@ -415,6 +444,7 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
   gather_issue_idx<kBU>(src, dst, tile * kBT, n_pairs, regs);
   gather_issue_rows<kBU>(pd, ps, regs);
   gather_issue_idx<kBU>(src, dst, (tile + gridDim.x) * kBT, n_pairs, regs);
+  regs.keep = gather_keep_bits<kBU>(tile * kBT, drop);
   for (; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t base = tile * kBT;
     gather_commit<kBT, kBU, true>(regs, base, drop, Z_hi, Z_lo);
@@ -465,6 +495,7 @@ decoder_bwd_tc_kernel(const int* __restrict__ src, const int* __restrict__ dst, 
     issue_z2((tile + gridDim.x) * kBT);
     gather_issue_rows<kBU>(pd, ps, regs);
     gather_issue_idx<kBU>(src, dst, (tile + 2 * static_cast<int64_t>(gridDim.x)) * kBT, n_pairs, regs);
+    regs.keep = gather_keep_bits<kBU>((tile + gridDim.x) * kBT, drop);     // next tile's masks, in the shadow of the MMAs
     // ---- dz1 epilogue: this thread holds unit 32q + lane of pairs 16g .. 16g+15; a warp stores 128 contiguous
     // bytes of one pair's row per instruction ----
     mbar_wait(bar1, it & 1);
