@@ -188,16 +188,20 @@ gemm_nt_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   }
-  if (warp >= 2 && warp < 6) {
-    // ===== epilogue: TMEM -> registers -> global; warp w owns TMEM lanes 32*(w%4) .. +31 =====
-    const int q = warp & 3;
+  if (warp >= 2) {
+    // ===== epilogue: TMEM -> registers -> global. A warp can only read TMEM lanes 32*(w%4) .. +31 (= 32 output rows); the
+    // 16 transform warps split the tile 4 lane quarters x 4 column groups of 32, so every warp stores kMT x 32 rows x 128 B.
+    // (Round 1 ran it on 4 warps: for the K = 128 layers, 4 k-blocks per 128 KB of output, the epilogue was most of the
+    // CTA's 17 us.) =====
+    static_assert(kXformWarps == 16 && kBN / 32 == 4, "epilogue mapping: 4 lane quarters x 4 column groups");
+    const int q = warp & 3, cg = (warp - 2) >> 2;
     if (n_iter > 0) {
       mbar_wait(tfull, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
 #pragma unroll 1
-    for (int hc = 0; hc < kMT * (kBN / 32); ++hc) {
-      const int h = hc / (kBN / 32), c = hc - h * (kBN / 32);
+    for (int h = 0; h < kMT; ++h) {
+      const int c = cg;
       const int row = m0 + h * kBM + q * 32 + lane;
       float scale = 1.f;
       float* out;
