@@ -219,8 +219,13 @@ def measure(ctx, workload, scale, steps, warmup, aug='default', cuda_graph=True,
     th.manual_seed(seed)
     spec, state, margs, data_how = build_state(ctx, workload, scale, seed)
     model = Net(margs).to(dev)
-    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5, capturable=cuda_graph)
-    loss_fn = th.nn.BCEWithLogitsLoss()
+    from dreamgnn_b200.optim import FusedAdam
+    if os.environ.get('DG_TORCH_TAIL') == '1':          # A/B: torch's own loss / clip / Adam launches
+        opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5, capturable=cuda_graph)
+        loss_fn = th.nn.BCEWithLogitsLoss()
+    else:                                               # what train() uses: fused BCE, fused clip + Adam
+        opt = FusedAdam(model.parameters(), lr=0.002, weight_decay=1e-5)
+        loss_fn = ops.FusedBCEWithLogitsLoss()
     aug_methods = FULL_AUG if aug == 'full' else ['edge_dropout', 'feature_noise']
     aug_params = aug_params_from_args(argparse.Namespace())
     closs = common_loss if spec['kind'] == 'dense' else common_loss_gram
@@ -525,7 +530,8 @@ def measure_rows(ctx, workload, scale, steps, warmup, single_gpu_ms=None, check_
     th.cuda.empty_cache()
     model.train()
     use_graph = os.environ.get('DG_ROWS_GRAPH', '1') != '0'
-    opt = th.optim.Adam(model.parameters(), lr=0.002, weight_decay=1e-5, capturable=use_graph)
+    from dreamgnn_b200.optim import FusedAdam
+    opt = FusedAdam(model.parameters(), lr=0.002, weight_decay=1e-5)
     th.manual_seed(4321 + ctx.rank)                                    # per-rank dropout / noise streams
     eager_step = lambda: D.train_iteration_partitioned(model, opt, state)
     step, launch = eager_step, 'eager launches (NCCL inside the step)'

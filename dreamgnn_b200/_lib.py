@@ -5,15 +5,22 @@ device, the call raises. Build with `python -m dreamgnn_b200.build`.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_ulonglong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_ulonglong, c_void_p
 
 import torch as th
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'lib', 'libdreamgnn.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _P = c_void_p
+
+
+class AdamTensor(Structure):
+    """dg_adam_tensor_t (include/dreamgnn.h): one parameter with its gradient and Adam moments."""
+    _fields_ = [('param', c_void_p), ('grad', c_void_p), ('exp_avg', c_void_p), ('exp_avg_sq', c_void_p), ('numel', c_int64)]
+
+
 _SIGNATURES = {
     'dg_abi_version': (c_int, []),
     'dg_last_error': (c_char_p, []),
@@ -56,6 +63,13 @@ _SIGNATURES = {
     'dg_attention_bwd_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'dg_attention_bwd_f32': (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_float, c_uint64, _P, _P,
                                      c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
+    'dg_bce_logits_workspace_bytes': (c_size_t, [c_int64]),
+    'dg_bce_logits_fwd_f32': (c_int, [_P, _P, c_int64, c_float, _P, _P, c_size_t, _P]),
+    'dg_bce_logits_bwd_f32': (c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
+    'dg_gram_common_loss_f64': (c_int, [_P, c_int64, c_int64, c_double, _P, _P, _P]),
+    'dg_adam_workspace_bytes': (c_size_t, [POINTER(AdamTensor), c_int]),
+    'dg_adam_clip_step_f32': (c_int, [POINTER(AdamTensor), c_int, _P, _P, c_double, c_double, c_double, c_double, c_double, c_double,
+                                      _P, _P, c_size_t, _P]),
     'dg_bench_read_rows': (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, _P]),
 }
 

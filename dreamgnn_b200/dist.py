@@ -407,6 +407,7 @@ def train_iteration_partitioned(model, optimizer, state, beta=0.001, grad_clip=1
                                 feature_noise_scale=0.05, augment=True):
     """train.py:250-300 on a row-partitioned graph. Returns the global loss (same value on every rank)."""
     model.train()
+    ops.begin_seed_pool(state.drug_feat.device)       # this iteration's dropout seeds: one launch
     if augment:
         enc = state.enc_graph.edge_dropout(edge_dropout_rate)
         knn = {k: a.edge_dropout(edge_dropout_rate) for k, a in state.knn.items()}
@@ -421,8 +422,8 @@ def train_iteration_partitioned(model, optimizer, state, beta=0.001, grad_clip=1
     local.backward()
     params = [p for p in model.parameters()]
     all_reduce_gradients(params)
-    th.nn.utils.clip_grad_norm_(params, grad_clip)
-    optimizer.step()
+    from .train import clip_and_step
+    clip_and_step(model, optimizer, grad_clip)
     with th.no_grad():
         total = all_reduce_sum(bce.detach()) + beta * common.detach()
     return total
@@ -456,6 +457,7 @@ class GraphedPartitionedIteration:
         self.graph = th.cuda.CUDAGraph()
         with th.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.loss = self._step()
+        ops.drop_seed_pool()                               # its buffer now belongs to the graph
         th.cuda.synchronize()
 
     def __call__(self):

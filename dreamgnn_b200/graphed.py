@@ -195,6 +195,7 @@ class GraphedIteration:
                     self.staged.refresh(augment_state(state, aug_methods, aug_params))
                 self.loss = self._step(self._live)
                 main.wait_stream(self._aug_stream)                       # join
+        ops.drop_seed_pool()                                             # its buffer now belongs to the graph
         if hasattr(model, 'parallel_routes'):
             model.parallel_routes = False                                # the branches are in the graph; eager calls stay serial
         self.launches_per_replay = _lib.launch_count() - launches0       # C-ABI kernels recorded into the graph

@@ -200,6 +200,14 @@ class GCMCLayer(nn.Module):
             out['rev-%s' % rating] = W[i]
         return out
 
+    def _rating_index(self, etype):
+        """Position in `rating_vals` of the rating behind an etype name ('3' or 'rev-3')."""
+        name = etype[4:] if etype.startswith('rev-') else etype
+        for i, rating in enumerate(self.rating_vals):
+            if to_etype_name(rating) == name:
+                return i
+        raise KeyError(etype)
+
     def forward(self, graph, drug_feat=None, dis_feat=None, Two_Stage=False):
         if self.agg != 'sum':
             raise NotImplementedError("only agg='sum' is usable downstream (as in the reference)")
@@ -213,6 +221,27 @@ class GCMCLayer(nn.Module):
                 seen.append(c[2])
 
         part = getattr(graph, 'partition', None)                     # row-partitioned graph: features hold the owned rows
+        memo = {}
+
+        def weight_stack(blk):
+            """[R, in, Dp] weights of a block's relations, message width zero-padded to the vector width. Shared-dims
+            branch: both node types' blocks use W = att @ basis in rating order, so it is padded once per layer and
+            shared (autograd then adds two gradients instead of un-stacking / un-padding / scattering each slice)."""
+            names = [c[1] for c in blk.etypes]
+            if self.W_r is None:
+                return _pad_cols(th.stack([weights[n] for n in names], dim=0), mult)
+            order = tuple(self._rating_index(n) for n in names)
+            if 'padded' not in memo:
+                memo['padded'] = _pad_cols(self.W, mult)
+            if order not in memo:
+                memo[order] = memo['padded'] if order == tuple(range(self.W.shape[0])) else memo['padded'][list(order)]
+            return memo[order]
+
+        def padded(w):
+            """Zero-padded copy of an output-layer weight, made once per forward (ifc is ufc with share_param)."""
+            if id(w) not in memo:
+                memo[id(w)] = _pad_cols(w, mult)
+            return memo[id(w)]
 
         def messages(dst_type):
             """Projection operands of one destination type: (block, x, [R, in, Dp] weights, [R * N_src] dropout(cj) scales)."""
@@ -220,9 +249,14 @@ class GCMCLayer(nn.Module):
             x = feats[blk.src_type]
             if part is None and x.size(0) != blk.n_src:
                 raise ValueError('%s features have %d rows for %d nodes' % (blk.src_type, x.size(0), blk.n_src))
-            wstack = th.stack([_pad_cols(weights[c[1]], mult) for c in blk.etypes], dim=0)   # [R, in, Dp]
-            cj = graph.nodes[blk.src_type].data['cj']
-            scale = th.stack([_flat_f32(self.conv.mods[c[1]].dropout(cj)) for c in blk.etypes], dim=0).reshape(-1)
+            wstack = weight_stack(blk)                                   # [R, in, Dp]
+            cj = _flat_f32(graph.nodes[blk.src_type].data['cj'])
+            drops = [self.conv.mods[c[1]].dropout for c in blk.etypes]
+            if all(d.p == drops[0].p and d.training == drops[0].training for d in drops):
+                # the R per-relation dropout(cj) draws (layers.py:222) as ONE draw over the [R, N_src] expansion
+                scale = F.dropout(cj.unsqueeze(0).expand(len(drops), -1), drops[0].p, drops[0].training).reshape(-1)
+            else:
+                scale = th.stack([d(cj) for d in drops], dim=0).reshape(-1)
             return blk, x, wstack, scale
 
         def aggregate(dst_type):
@@ -261,7 +295,7 @@ class GCMCLayer(nn.Module):
             else:                                                  # activation + dropout in one launch (K7)
                 y = ops.act_dropout(agg, code[0], code[1], p=self.dropout.p, training=self.training)
             fc = self.ifc if dst_type == 'drug' else self.ufc
-            w = _pad_cols(fc.weight, mult) if y.shape[1] != D else fc.weight
+            w = padded(fc.weight) if y.shape[1] != D else fc.weight
             return ops.linear(y, w, fc.bias)
 
         missing = [t for t in ('drug', 'disease') if t not in seen]
@@ -456,7 +490,7 @@ class MLPDecoder(nn.Module):
         seed = 0
         if self.training and self.dropout.p > 0:
             # drawn on device (no host sync, and a captured CUDA graph gets a fresh seed on every replay)
-            seed = th.randint(0, 2 ** 62, (1,), device=pd.device, dtype=th.int64)
+            seed = ops.fresh_seed(pd.device)
         return ops.decoder_mlp(pd, ps, self.lin2.weight, self.lin2.bias, self.lin3.weight, self.lin3.bias, pairs,
                                p=self.dropout.p, seed=seed, training=self.training)
 

@@ -43,7 +43,8 @@ class Net(nn.Module):
         acc = None
         for depth, layer in enumerate(self.TGCN, start=1):
             drug, dis = layer(enc_graph, drug, dis, two_stage)
-            acc = (drug, dis) if acc is None else (acc[0] + drug / float(depth), acc[1] + dis / float(depth))
+            # out += o / (l + 1) (model.py:70-76) as one scaled add
+            acc = (drug, dis) if acc is None else (th.add(acc[0], drug, alpha=1.0 / depth), th.add(acc[1], dis, alpha=1.0 / depth))
         return acc
 
     def _fuse(self, topo, feat):

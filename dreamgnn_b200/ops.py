@@ -295,7 +295,7 @@ class GramCommonLoss(th.autograd.Function):
         loss = (|G11|^2 + |G22|^2 - 2 |G12|^2) / n^2 = sum(G * G * S) / n^2,  S = [[+1, -1], [-1, +1]]
         dL/dZ = (4 / n^2) Z (G * S);   dc = (gz - z <z, gz>) / |c|;   dx = dc - colmean(dc)
 
-    ~25 launches per call against ~95 for the autograd-traced torch expression; same value (float64 accumulation)."""
+    ~18 launches per call against ~95 for the autograd-traced torch expression; same value (float64 accumulation)."""
 
     @staticmethod
     def forward(ctx, emb1, emb2):
@@ -310,11 +310,10 @@ class GramCommonLoss(th.autograd.Function):
                                                 z.data_ptr() + i * d * 8, 2 * d, inv.data_ptr() + i * n * 8, L.stream()),
                     'center_normalize')
         g = z.t() @ z                                                     # [2d, 2d] float64
-        gs = g.clone()                                                    # G * S: the off-diagonal blocks negated
-        blocks = gs.view(2, d, 2, d)
-        blocks[0, :, 1, :].neg_()
-        blocks[1, :, 0, :].neg_()
-        loss = ((g * gs).sum() / float(n) / float(n)).float()
+        gs = th.empty((2 * d, 2 * d), dtype=th.float64, device=dev)       # G * S: the off-diagonal blocks negated
+        loss = th.empty((), dtype=th.float32, device=dev)
+        L.check(lib.dg_gram_common_loss_f64(g.data_ptr(), g.stride(0), d, float(n), L.ptr(gs), L.ptr(loss), L.stream()),
+                'gram_common_loss')                                       # loss = sum(G * G * S) / n^2, one launch
         ctx.save_for_backward(z, inv, gs)
         ctx.shape = (n, d)
         return loss
@@ -348,13 +347,105 @@ def gram_common_loss(emb1, emb2):
 
 
 # ------------------------------------------------------------------------------------------------
+# binary cross entropy over the scored pairs (csrc/loss.cu)
+# ------------------------------------------------------------------------------------------------
+class BCEWithLogitsFunction(th.autograd.Function):
+    """mean BCE-with-logits (train.py:291; targets smoothed as train.py:15-23): two launches forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, logits, target, smoothing):
+        lib = L.load()
+        n = logits.numel()
+        loss = th.empty((), dtype=th.float32, device=logits.device)
+        ws = L.workspace(lib.dg_bce_logits_workspace_bytes(n), logits.device)
+        L.check(lib.dg_bce_logits_fwd_f32(L.ptr(logits, th.float32, 'logits'), L.ptr(target, th.float32, 'target'), n,
+                                          float(smoothing), L.ptr(loss), L.ptr(ws), ws.numel(), L.stream()), 'bce_logits_fwd')
+        ctx.save_for_backward(logits, target)
+        ctx.smoothing = float(smoothing)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.load()
+        logits, target = ctx.saved_tensors
+        dx = th.empty_like(logits)
+        gout = gout.to(th.float32).contiguous()
+        L.check(lib.dg_bce_logits_bwd_f32(L.ptr(logits), L.ptr(target), logits.numel(), ctx.smoothing, L.ptr(gout), L.ptr(dx),
+                                          L.stream()), 'bce_logits_bwd')
+        return dx, None, None
+
+
+def bce_with_logits(logits, target, smoothing=0.0):
+    """mean(binary_cross_entropy_with_logits(logits, target * (1 - s) + s / 2)) for fp32 CUDA tensors of equal shape."""
+    if not (isinstance(logits, th.Tensor) and logits.is_cuda and target.is_cuda):
+        raise RuntimeError('dreamgnn_b200.bce_with_logits needs CUDA tensors (no CPU fallback)')
+    if logits.shape != target.shape or logits.numel() == 0:
+        raise ValueError('bce_with_logits: logits %s and target %s must have the same non-empty shape'
+                         % (tuple(logits.shape), tuple(target.shape)))
+    return BCEWithLogitsFunction.apply(logits.to(th.float32).contiguous(), target.to(th.float32).contiguous(), float(smoothing))
+
+
+class FusedBCEWithLogitsLoss(th.nn.Module):
+    """Drop-in for nn.BCEWithLogitsLoss() (mean reduction) and train.py's LabelSmoothingBCELoss(smoothing)."""
+
+    def __init__(self, smoothing=0.0):
+        super().__init__()
+        self.smoothing = float(smoothing)
+
+    def forward(self, pred, target):
+        return bce_with_logits(pred, target, self.smoothing)
+
+
+# ------------------------------------------------------------------------------------------------
 # fused row kernels (csrc/fused.cu)
 # ------------------------------------------------------------------------------------------------
 ACT_CODES = {None: 0, 'identity': 0, 'leaky': 1, 'relu': 2}
 
 
+class _SeedPool:
+    """Seeds of one training iteration drawn by ONE launch (`begin_seed_pool`, called at the top of the iteration on its
+    main stream) instead of one `randint` launch in front of each of the ~15 fused dropout kernels."""
+    SIZE = 32
+
+    def __init__(self, device):
+        self.buf = th.randint(0, 2 ** 62, (self.SIZE,), device=device, dtype=th.int64)
+        self.next = 0
+        self.capturing = th.cuda.is_current_stream_capturing()
+        self.stream = th.cuda.current_stream(device)
+        self.event = th.cuda.Event()
+        self.event.record(self.stream)
+
+
+_SEED_POOLS = {}
+
+
+def begin_seed_pool(device):
+    """Draw this iteration's dropout seeds (one launch). Call on the stream the iteration's branches fork from."""
+    device = th.device(device)
+    if device.type == 'cuda':
+        _SEED_POOLS[device] = _SeedPool(device)
+
+
+def drop_seed_pool(device=None):
+    """Forget the pool (after a CUDA-graph capture its buffer belongs to the graph's memory and is rewritten only by replays)."""
+    if device is None:
+        _SEED_POOLS.clear()
+    else:
+        _SEED_POOLS.pop(th.device(device), None)
+
+
 def fresh_seed(device):
-    """A dropout seed drawn on the device (no host sync; a captured CUDA graph gets a fresh one on every replay)."""
+    """A dropout seed drawn on the device (no host sync; a captured CUDA graph gets a fresh one on every replay): the next
+    slot of the iteration's pool when there is one (same capture state, not used up), else its own `randint` launch."""
+    device = th.device(device)
+    pool = _SEED_POOLS.get(device)
+    if pool is not None and pool.next < pool.SIZE and pool.capturing == th.cuda.is_current_stream_capturing():
+        cur = th.cuda.current_stream(device)
+        if cur != pool.stream:
+            cur.wait_event(pool.event)                 # a parallel branch forked before / beside the draw
+        seed = pool.buf[pool.next:pool.next + 1]
+        pool.next += 1
+        return seed
     return th.randint(0, 2 ** 62, (1,), device=device, dtype=th.int64)
 
 

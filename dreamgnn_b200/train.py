@@ -12,8 +12,10 @@ import torch as th
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .augmentation import augment_graph_data
 from .model import Net
+from .optim import FusedAdam
 from .utils import common_loss, common_loss_gram, setup_seed  # noqa: F401
 
 FIXED_SEEDS = [77, 31415, 888, 1001, 9999, 0, 42, 123, 2024, 7]      # train.py:456
@@ -112,6 +114,8 @@ def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_param
     """One training iteration exactly as train.py:250-300; returns the (device) loss tensor. `aug` may carry
     an augmentation drawn ahead of time (graphed.GraphedIteration pipelines it beside the previous iteration)."""
     model.train()
+    if state.labels.is_cuda:
+        ops.begin_seed_pool(state.labels.device)      # this iteration's dropout seeds: one launch
     if aug is None:
         aug = augment_state(state, aug_methods, aug_params)
     pred, drug_out, drug_sim_out, dis_out, dis_sim_out = model(
@@ -122,9 +126,17 @@ def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_param
     total = rel + beta * (common_loss_fn(drug_out, drug_sim_out) + common_loss_fn(dis_out, dis_sim_out))
     optimizer.zero_grad()
     total.backward()
-    nn.utils.clip_grad_norm_(model.parameters(), grad_clip)
-    optimizer.step()
+    clip_and_step(model, optimizer, grad_clip)
     return total
+
+
+def clip_and_step(model, optimizer, grad_clip):
+    """train.py:297-300. `optim.FusedAdam` does both in two launches; any other optimizer takes torch's two calls."""
+    if hasattr(optimizer, 'clip_and_step'):
+        optimizer.clip_and_step(grad_clip)
+    else:
+        nn.utils.clip_grad_norm_(model.parameters(), grad_clip)
+        optimizer.step()
 
 
 def make_train_state(dataset, cv, dev):
@@ -154,10 +166,8 @@ def train(args, dataset, cv):
     state = make_train_state(dataset, cv, dev)
     train_data_dict, test_data_dict = {'test': cv_data['train']}, {'test': cv_data['test']}
     model = Net(args=args).to(dev)
-    if getattr(args, 'label_smoothing', 0.0) > 0:
-        rel_loss_fn = LabelSmoothingBCELoss(smoothing=args.label_smoothing)
-    else:
-        rel_loss_fn = nn.BCEWithLogitsLoss()
+    # nn.BCEWithLogitsLoss / LabelSmoothingBCELoss (train.py:206-209) as one fused kernel each way
+    rel_loss_fn = ops.FusedBCEWithLogitsLoss(smoothing=max(float(getattr(args, 'label_smoothing', 0.0)), 0.0))
     use_graph = bool(getattr(args, 'cuda_graph', False))
     entry_stream = th.cuda.current_stream() if use_graph else None
     if use_graph and entry_stream == th.cuda.default_stream():
@@ -165,7 +175,7 @@ def train(args, dataset, cv):
     # graph mode: the learning rate lives in a device tensor, which the captured Adam step reads on every replay and
     # ReduceLROnPlateau updates in place -- a scheduler step takes effect without re-capturing
     lr = th.tensor(float(args.train_lr), device=dev) if use_graph else args.train_lr
-    optimizer = th.optim.Adam(model.parameters(), lr=lr, weight_decay=args.weight_decay, capturable=use_graph)
+    optimizer = FusedAdam(model.parameters(), lr=lr, weight_decay=args.weight_decay)     # th.optim.Adam + clip, fused
     scheduler = th.optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'max', patience=500, factor=0.5)
     aug_methods = getattr(args, 'aug_methods', ['edge_dropout', 'feature_noise'])
     aug_params = aug_params_from_args(args)

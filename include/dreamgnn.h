@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 4
+#define DG_ABI_VERSION 5
 
 #define DG_OK 0
 #define DG_ERR_INVALID_ARGUMENT (-1)
@@ -261,6 +261,46 @@ DG_API int dg_attention_bwd_f32(const float* za, int64_t lda, const float* zb, i
                          const uint64_t* seed_dev, const float* dout, int64_t lddo, const float* dbeta, float* dza,
                          int64_t ldda, float* dzb, int64_t lddb, float* out_params, void* workspace,
                          size_t workspace_bytes, dg_stream_t stream);
+
+/* ---- loss and optimiser tail of the iteration (csrc/loss.cu, csrc/optim.cu) ------------------ */
+/* Mean binary cross entropy with logits over n scored pairs, targets optionally smoothed to t (1 - s) + s / 2
+ * (nn.BCEWithLogitsLoss at train.py:291, LabelSmoothingBCELoss train.py:15-23): *loss (device float) =
+ * mean_i [max(x, 0) - x t + log1p(exp(-|x|))], summed in float64 in a fixed order. Two launches. */
+DG_API size_t dg_bce_logits_workspace_bytes(int64_t n);
+DG_API int dg_bce_logits_fwd_f32(const float* logits, const float* target, int64_t n, float smoothing, float* loss,
+                          void* workspace, size_t workspace_bytes, dg_stream_t stream);
+/* Its gradient: dlogits[i] = *gout * (sigmoid(x_i) - t_i) / n; gout is a device float (the upstream gradient). */
+DG_API int dg_bce_logits_bwd_f32(const float* logits, const float* target, int64_t n, float smoothing, const float* gout,
+                          float* dlogits, dg_stream_t stream);
+/* Tail of common_loss (utils.py:87-95) in Gram form: for G = Z^T Z [2d, 2d] float64 (leading dimension ldg) of the two
+ * centred, normalised embeddings side by side, gs [2d, 2d] (dense) = G * S with S = +1 on the two diagonal d x d blocks
+ * and -1 off them, and *loss (device float) = sum(G * gs) / n_rows^2 = (|G11|^2 + |G22|^2 - 2 |G12|^2) / n^2. One launch. */
+DG_API int dg_gram_common_loss_f64(const double* G, int64_t ldg, int64_t d, double n_rows, double* gs, float* loss,
+                            dg_stream_t stream);
+
+/* nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step() (train.py:297-300) over a list of fp32
+ * tensors in two launches per DG_ADAM_MAX_TENSORS_PER_LAUNCH tensors: the global gradient norm from per-chunk float64
+ * partial sums added in a fixed order, then per element
+ *   g <- g * min(1, max_norm / (norm + 1e-6))        (written back to grad; max_norm <= 0: no clipping)
+ *   g' = g + weight_decay * p;  m <- m + (g' - m)(1 - beta1);  v <- beta2 v + (1 - beta2) g'^2
+ *   p <- p - lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
+ * `tensors` is a HOST array (its entries are copied into the kernel arguments); every pointer inside is a device pointer
+ * to `numel` contiguous floats. `step` (device float) holds t - 1 on entry and is incremented once per call. The learning
+ * rate is read from lr_dev (device float) when non-NULL -- a scheduler can change it under a captured CUDA graph -- else
+ * `lr`. Hyper-parameters are doubles because torch derives 1 - beta and the bias corrections from Python floats before
+ * rounding to fp32 once. norm_out (device float, may be NULL) receives the gradient norm before clipping. */
+typedef struct {
+  void* param;
+  void* grad;
+  void* exp_avg;
+  void* exp_avg_sq;
+  int64_t numel;
+} dg_adam_tensor_t;
+#define DG_ADAM_MAX_TENSORS_PER_LAUNCH 48
+DG_API size_t dg_adam_workspace_bytes(const dg_adam_tensor_t* tensors, int n_tensors);
+DG_API int dg_adam_clip_step_f32(const dg_adam_tensor_t* tensors, int n_tensors, float* step, const float* lr_dev, double lr,
+                          double beta1, double beta2, double eps, double weight_decay, double max_norm, float* norm_out,
+                          void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
 /* ---- measurement support ------------------------------------------------------------------- */
 /* Read-bandwidth microbenchmark with the SpMM's access shape (scripts/l2_peak.py -> profiles/l2_peak.json): every warp

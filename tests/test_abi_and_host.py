@@ -53,6 +53,31 @@ def test_no_cpu_fallback():
                         th.randn(1), None)
     with pytest.raises(RuntimeError):
         layers.adjacency_csr(th.eye(3).to_sparse())
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.bce_with_logits(th.zeros(3), th.zeros(3))
+    from dreamgnn_b200.optim import FusedAdam
+    p = th.zeros(4, requires_grad=True)
+    p.grad = th.ones(4)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        FusedAdam([p]).step()
+    assert th.equal(p.detach(), th.zeros(4))
+
+
+def test_fused_adam_keeps_torch_adams_contract():
+    """Same param_groups / defaults / state_dict layout as torch.optim.Adam (checkpoints interchange); options the
+    kernel does not implement are refused at construction; the seed pool is a CUDA-only shortcut."""
+    from dreamgnn_b200.optim import FusedAdam
+    p = th.zeros(4, requires_grad=True)
+    opt = FusedAdam([p], lr=0.002, weight_decay=1e-5)
+    ref = th.optim.Adam([p], lr=0.002, weight_decay=1e-5)
+    g, r = opt.param_groups[0], ref.param_groups[0]
+    assert {k: g[k] for k in ('lr', 'betas', 'eps', 'weight_decay')} == {k: r[k] for k in ('lr', 'betas', 'eps', 'weight_decay')}
+    assert g['capturable'] is True and isinstance(opt, th.optim.Adam)
+    assert set(opt.state_dict()) == set(ref.state_dict())
+    with pytest.raises(ValueError, match='amsgrad'):
+        FusedAdam([p], amsgrad=True)
+    ops.begin_seed_pool('cpu')                                        # no-op off CUDA
+    assert ops.fresh_seed(th.device('cpu')).shape == (1,)
 
 
 def _args(g, name):
