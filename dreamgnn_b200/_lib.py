@@ -51,9 +51,9 @@ _SIGNATURES = {
     'dg_gemm_f32': (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                             c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
     'dg_colsum_workspace_bytes': (c_size_t, [c_int64, c_int64]),
-    'dg_colsum_f32': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    'dg_colsum_f32': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P, _P]),
     'dg_center_normalize_f64': (c_int, [_P, c_int64, _P, c_int64, c_int64, c_double, _P, c_int64, _P, _P]),
-    'dg_center_normalize_bwd_f64': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P]),
+    'dg_center_normalize_bwd_f64': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, c_double, _P]),
     'dg_topk_rows_f64': (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P, _P]),
     'dg_knn_graph_workspace_bytes': (c_size_t, [c_int64, c_int]),
     'dg_knn_graph_from_neighbors': (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
@@ -67,6 +67,9 @@ _SIGNATURES = {
     'dg_bce_logits_fwd_f32': (c_int, [_P, _P, c_int64, c_float, _P, _P, c_size_t, _P]),
     'dg_bce_logits_bwd_f32': (c_int, [_P, _P, c_int64, c_float, _P, _P, _P]),
     'dg_gram_common_loss_f64': (c_int, [_P, c_int64, c_int64, c_double, _P, _P, _P]),
+    'dg_basis_combine_fwd_f32': (c_int, [_P, _P, c_int, c_int, c_int64, c_int64, c_int64, _P, _P]),
+    'dg_basis_combine_bwd_workspace_bytes': (c_size_t, [c_int64, c_int64]),
+    'dg_basis_combine_bwd_f32': (c_int, [_P, _P, _P, c_int, c_int, c_int64, c_int64, c_int64, _P, _P, _P, c_size_t, _P]),
     'dg_adam_workspace_bytes': (c_size_t, [POINTER(AdamTensor), c_int]),
     'dg_adam_clip_step_f32': (c_int, [POINTER(AdamTensor), c_int, _P, _P, c_double, c_double, c_double, c_double, c_double, c_double,
                                       _P, _P, c_size_t, _P]),

@@ -11,6 +11,7 @@ namespace {
 
 constexpr int kColChunk = 128;    // columns per CTA column-chunk: 32 lanes x float4
 constexpr int kColsumWarps = 8;
+constexpr int64_t kColsumOneLaunchRows = 16384;   // below this the finishing launch costs more than it computes
 
 __host__ __device__ inline int colsum_slabs(int64_t n_rows, int64_t d) {
   const int chunks = static_cast<int>((d + kColChunk - 1) / kColChunk);
@@ -26,7 +27,8 @@ __host__ __device__ inline int colsum_slabs(int64_t n_rows, int64_t d) {
 template <bool kGate, bool kWrite>
 __global__ void __launch_bounds__(kColsumWarps * 32)
 colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ gate, int64_t ldg,
-                      float* __restrict__ y, int64_t ldy, int64_t n_rows, int d, float* __restrict__ partial) {
+                      float* __restrict__ y, int64_t ldy, int64_t n_rows, int d, float* __restrict__ partial,
+                      int* __restrict__ tickets, float* __restrict__ out) {
   __shared__ float4 red[kColsumWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * kColChunk + lane * 4;
@@ -79,6 +81,41 @@ colsum_partial_kernel(const float* __restrict__ x, int64_t ldx, const float* __r
     }
     *reinterpret_cast<float4*>(partial + static_cast<int64_t>(blockIdx.y) * d + col) = s;
   }
+  if (tickets == nullptr) return;                    // two-launch form: colsum_finish_kernel adds the slabs
+  // One-launch form: the CTA that finishes LAST among this column chunk's slabs adds the slab partials -- in slab order,
+  // so the result does not depend on which CTA that is. (Matrices of a few hundred rows: the second launch costs more
+  // than both kernels' work, on a dependency chain that has ~40 of these per training iteration.)
+  __shared__ int is_last;
+  __shared__ double fin[2][kColChunk];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(tickets + blockIdx.x, 1);
+    is_last = (t == static_cast<int>(gridDim.y) - 1);
+    if (is_last) tickets[blockIdx.x] = 0;            // zero again for the next call / graph replay
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int c = threadIdx.x & (kColChunk - 1), half = threadIdx.x >> 7;       // 256 threads: 128 columns x 2 slab ranges
+  const int ccol = blockIdx.x * kColChunk + c;
+  const int per_half = (slabs + 1) / 2;
+  const int s0 = half * per_half, s1 = min(slabs, s0 + per_half);
+  double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (ccol < d) {
+    int i = s0;
+    for (; i + 7 < s1; i += 8) {                      // eight independent L2 loads in flight
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + static_cast<int64_t>(i + u) * d + ccol);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += v[u];
+    }
+    for (; i < s1; ++i) a[0] += __ldcg(partial + static_cast<int64_t>(i) * d + ccol);
+  }
+  fin[half][c] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (half == 0 && ccol < d) out[ccol] = static_cast<float>(fin[0][c] + fin[1][c]);
 }
 
 // out[col] = sum of the slab partials in a fixed order: 32 warps each sum a contiguous range of slabs for 32 columns
@@ -147,7 +184,8 @@ center_normalize_kernel(const float* __restrict__ x, int64_t ldx, const float* _
 // gradient w.r.t. the centred row c (before the mean is subtracted again): dc = (gz - z (z . gz)) * inv, fp32 out
 __global__ void __launch_bounds__(256)
 center_normalize_bwd_kernel(const double* __restrict__ gz, int64_t ldgz, const double* __restrict__ z, int64_t ldz,
-                            const double* __restrict__ inv_norm, int64_t n_rows, int d, float* __restrict__ dc, int64_t lddc) {
+                            const double* __restrict__ inv_norm, int64_t n_rows, int d, float* __restrict__ dc, int64_t lddc,
+                            const float* __restrict__ gout, double scale) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
@@ -161,7 +199,8 @@ center_normalize_bwd_kernel(const double* __restrict__ gz, int64_t ldgz, const d
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(kFull, dot, o);
-  const double inv = inv_norm[row];
+  // the upstream scalar gradient and the loss's constant factor ride along (the product is linear in gz)
+  const double inv = inv_norm[row] * (gout ? static_cast<double>(__ldg(gout)) * scale : scale);
   float* dr = dc + row * lddc;
   for (int c = lane * 4; c < d; c += kColChunk) {
     const double2 g0 = *reinterpret_cast<const double2*>(gr + c), g1 = *reinterpret_cast<const double2*>(gr + c + 2);
@@ -186,7 +225,7 @@ size_t dg_colsum_workspace_bytes(int64_t n_rows, int64_t d) {
 }
 
 int dg_colsum_f32(const float* x, int64_t ldx, const float* gate, int64_t ldg, float* y, int64_t ldy, int64_t n_rows,
-                  int64_t d, float* out, void* workspace, size_t workspace_bytes, dg_stream_t stream) {
+                  int64_t d, float* out, void* workspace, size_t workspace_bytes, int32_t* tickets, dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(n_rows >= 0 && d > 0 && d <= (1 << 20), "bad shape");
   DG_REQUIRE(x != nullptr && out != nullptr, "null pointer");
@@ -198,7 +237,14 @@ int dg_colsum_f32(const float* x, int64_t ldx, const float* gate, int64_t ldg, f
     DG_CHECK_CUDA(cudaMemsetAsync(out, 0, static_cast<size_t>(d) * sizeof(float), st));
     return DG_OK;
   }
-  const int slabs = colsum_slabs(n_rows, d);
+  int slabs = colsum_slabs(n_rows, d);
+  // one launch (last CTA adds the slabs) when the caller lends zeroed tickets and the matrix is small enough for the
+  // launch, not the bandwidth, to be what costs; then with at least four rows per warp, so that few slabs are left to add
+  int* tk = (tickets != nullptr && n_rows <= kColsumOneLaunchRows) ? tickets : nullptr;
+  if (tk != nullptr) {
+    const int64_t cap = (n_rows + 4 * kColsumWarps - 1) / (4 * kColsumWarps);
+    if (slabs > cap) slabs = static_cast<int>(cap < 1 ? 1 : cap);
+  }
   Workspace ws(workspace, workspace_bytes);
   float* partial = ws.take<float>(static_cast<size_t>(slabs) * d);
   if (partial == nullptr) {
@@ -208,14 +254,15 @@ int dg_colsum_f32(const float* x, int64_t ldx, const float* gate, int64_t ldg, f
   const dim3 grid(static_cast<unsigned>((d + kColChunk - 1) / kColChunk), static_cast<unsigned>(slabs));
   const int di = static_cast<int>(d);
   if (gate != nullptr && y != nullptr)
-    colsum_partial_kernel<true, true><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, gate, ldg, y, ldy, n_rows, di, partial);
+    colsum_partial_kernel<true, true><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, gate, ldg, y, ldy, n_rows, di, partial, tk, out);
   else if (gate != nullptr)
-    colsum_partial_kernel<true, false><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, gate, ldg, nullptr, 0, n_rows, di, partial);
+    colsum_partial_kernel<true, false><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, gate, ldg, nullptr, 0, n_rows, di, partial, tk, out);
   else if (y != nullptr)
-    colsum_partial_kernel<false, true><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, nullptr, 0, y, ldy, n_rows, di, partial);
+    colsum_partial_kernel<false, true><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, nullptr, 0, y, ldy, n_rows, di, partial, tk, out);
   else
-    colsum_partial_kernel<false, false><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, nullptr, 0, nullptr, 0, n_rows, di, partial);
+    colsum_partial_kernel<false, false><<<grid, kColsumWarps * 32, 0, st>>>(x, ldx, nullptr, 0, nullptr, 0, n_rows, di, partial, tk, out);
   DG_CHECK_LAUNCH("colsum_partial");
+  if (tk != nullptr) return DG_OK;
   colsum_finish_kernel<<<static_cast<unsigned>((d + 31) / 32), 32 * kFinishGroups, 0, st>>>(partial, slabs, di, out);
   DG_CHECK_LAUNCH("colsum_finish");
   return DG_OK;
@@ -236,7 +283,8 @@ int dg_center_normalize_f64(const float* x, int64_t ldx, const float* colsum, in
 }
 
 int dg_center_normalize_bwd_f64(const double* gz, int64_t ldgz, const double* z, int64_t ldz, const double* inv_norm,
-                                int64_t n_rows, int64_t d, float* dc, int64_t lddc, dg_stream_t stream) {
+                                int64_t n_rows, int64_t d, float* dc, int64_t lddc, const float* gout, double scale,
+                                dg_stream_t stream) {
   using namespace dg;
   DG_REQUIRE(n_rows >= 0 && d > 0, "bad shape");
   if (n_rows == 0) return DG_OK;
@@ -245,7 +293,8 @@ int dg_center_normalize_bwd_f64(const double* gz, int64_t ldgz, const double* z,
              "gz / z rows must be 16-byte aligned, d % 4 == 0");
   DG_REQUIRE(lddc % 4 == 0 && lddc >= d && aligned16(dc), "dc rows must be 16-byte aligned");
   const unsigned blocks = static_cast<unsigned>((n_rows + 7) / 8);
-  center_normalize_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(gz, ldgz, z, ldz, inv_norm, n_rows, static_cast<int>(d), dc, lddc);
+  center_normalize_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(gz, ldgz, z, ldz, inv_norm, n_rows, static_cast<int>(d), dc, lddc,
+                                                                      gout, scale);
   DG_CHECK_LAUNCH("center_normalize_bwd");
   return DG_OK;
 }

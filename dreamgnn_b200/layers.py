@@ -191,7 +191,14 @@ class GCMCLayer(nn.Module):
         the per-relation module's own parameter otherwise (layers.py:86-97)."""
         if self.W_r is None:
             return {et: m.weight for et, m in self.conv.mods.items()}
-        W = th.matmul(self.att, self.basis.view(self.basis_units, -1)).view(-1, self.user_in_units, self.msg_units)
+        if self.att.is_cuda:
+            # one elementwise kernel each way, written at the padded message width the aggregation wants (K2)
+            mult = MESSAGE_PAD or (8 if MESSAGE_DTYPE == th.bfloat16 else 4)
+            self.W_padded = ops.basis_combine(self.att, self.basis, mult)
+            W = self.W_padded[:, :, :self.msg_units]
+        else:
+            W = th.matmul(self.att, self.basis.view(self.basis_units, -1)).view(-1, self.user_in_units, self.msg_units)
+            self.W_padded = None
         self.W = W
         out = {}
         for i, rating in enumerate(self.rating_vals):
@@ -232,7 +239,7 @@ class GCMCLayer(nn.Module):
                 return _pad_cols(th.stack([weights[n] for n in names], dim=0), mult)
             order = tuple(self._rating_index(n) for n in names)
             if 'padded' not in memo:
-                memo['padded'] = _pad_cols(self.W, mult)
+                memo['padded'] = self.W_padded if self.W_padded is not None else _pad_cols(self.W, mult)
             if order not in memo:
                 memo[order] = memo['padded'] if order == tuple(range(self.W.shape[0])) else memo['padded'][list(order)]
             return memo[order]

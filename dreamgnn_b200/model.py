@@ -37,6 +37,7 @@ class Net(nn.Module):
         self.attention = L.Attention(args.gcn_out_units, dropout_rate=args.attention_dropout)
         self.decoder = L.MLPDecoder(in_units=args.gcn_out_units, dropout_rate=args.dropout)
         self.parallel_routes = False        # not part of the reference API: see `embed`
+        self.routes_ready = None
 
     def _topology_route(self, enc_graph, drug, dis, two_stage):
         """Stacked GCMC layers with the 1/(l+1)-weighted sum of their outputs (model.py:67-76)."""
@@ -65,6 +66,12 @@ class Net(nn.Module):
                 lambda: self._topology_route(enc_graph, drug_feat, dis_feat, Two_Stage),
                 lambda: self.FGCN(drug_graph, drug_sim_feat, dis_graph, disease_sim_feat, drug_feature_graph,
                                   disease_feature_graph)[:2]])
+        # with parallel branches on, mark the point where the four route outputs exist: the common losses (train.py:292-293)
+        # depend on nothing later and can run beside the attention + decoder (train.train_iteration forks there)
+        self.routes_ready = None
+        if self.parallel_routes and drug_feat.is_cuda:
+            self.routes_ready = th.cuda.Event()
+            self.routes_ready.record()
         return (drug_out, drug_sim_out, dis_out, dis_sim_out,
                 self._fuse(drug_out, drug_sim_out), self._fuse(dis_out, dis_sim_out))
 

@@ -259,6 +259,29 @@ def branches(fns):
 # ------------------------------------------------------------------------------------------------
 # row-streaming helpers (rowops.cu)
 # ------------------------------------------------------------------------------------------------
+# Zero-initialised int32 tickets lent to kernels that finish in their last CTA (dg_colsum_f32): handed out round-robin from
+# one persistent pool per device, so two calls that may be in flight at the same time (parallel stream branches, or nodes
+# of one captured graph) never share a slot; every kernel leaves its tickets zero again.
+_TICKET_POOL = {}
+_TICKET_SLOTS = 8192
+
+
+def _tickets(device, count):
+    """Device address of `count` zeroed tickets (None when the request is larger than a slot run)."""
+    if count > 64:
+        return None
+    pool = _TICKET_POOL.get(device)
+    if pool is None or (pool[2] != th.cuda.is_current_stream_capturing() and pool[2]):
+        # (a pool first allocated during a graph capture lives in that graph's memory: make a fresh one outside it)
+        buf = th.zeros(_TICKET_SLOTS, dtype=th.int32, device=device)
+        pool = _TICKET_POOL[device] = [buf, 0, th.cuda.is_current_stream_capturing()]
+    if pool[1] + count > _TICKET_SLOTS:
+        pool[1] = 0
+    addr = pool[0].data_ptr() + 4 * pool[1]
+    pool[1] += count
+    return addr
+
+
 def _rows_ok(t):
     return (t.dim() == 2 and t.dtype == th.float32 and t.stride(1) == 1 and t.shape[1] % 4 == 0
             and t.stride(0) % 4 == 0 and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0)
@@ -281,7 +304,7 @@ def colsum(x, gate=None, want_masked=False):
     ws = L.workspace(lib.dg_colsum_workspace_bytes(n, d), x.device)
     L.check(lib.dg_colsum_f32(x.data_ptr(), x.stride(0), None if gate is None else gate.data_ptr(),
                               0 if gate is None else gate.stride(0), L.ptr(y), d, n, d, L.ptr(out), L.ptr(ws), ws.numel(),
-                              L.stream()), 'colsum')
+                              _tickets(x.device, (d + 127) // 128), L.stream()), 'colsum')
     if want_masked:
         return (x if y is None else y), out
     return out
@@ -323,7 +346,8 @@ class GramCommonLoss(th.autograd.Function):
         lib = L.load()
         z, inv, gs = ctx.saved_tensors
         n, d = ctx.shape
-        gz = z @ (gs * (gout.double() * (4.0 / float(n) / float(n))))      # [n, 2d] float64
+        gz = z @ gs                                                       # [n, 2d] float64; dL/dZ = gz * gout * 4 / n^2
+        gout = gout.reshape(()).to(th.float32)
         grads = []
         for i in range(2):
             if not ctx.needs_input_grad[i]:
@@ -331,7 +355,8 @@ class GramCommonLoss(th.autograd.Function):
                 continue
             dc = th.empty((n, d), dtype=th.float32, device=z.device)
             L.check(lib.dg_center_normalize_bwd_f64(gz.data_ptr() + i * d * 8, 2 * d, z.data_ptr() + i * d * 8, 2 * d,
-                                                    inv.data_ptr() + i * n * 8, n, d, L.ptr(dc), d, L.stream()),
+                                                    inv.data_ptr() + i * n * 8, n, d, L.ptr(dc), d, L.ptr(gout),
+                                                    4.0 / float(n) / float(n), L.stream()),
                     'center_normalize_bwd')
             grads.append(dc.sub_(colsum(dc) / float(n)))
         return tuple(grads)
@@ -344,6 +369,68 @@ def gram_common_loss(emb1, emb2):
     if emb1.shape != emb2.shape or not (_rows_ok(emb1) and _rows_ok(emb2)):
         raise ValueError('gram_common_loss: two [n, d] fp32 matrices with 16-byte aligned rows expected')
     return GramCommonLoss.apply(emb1, emb2)
+
+
+# ------------------------------------------------------------------------------------------------
+# basis decomposition of the GCMC relation weights (csrc/basis.cu)
+# ------------------------------------------------------------------------------------------------
+class BasisCombineFunction(th.autograd.Function):
+    """W [R, in, Dp] = sum_b att[r, b] * basis[b], message width zero-padded D -> Dp in the same pass (layers.py:120-121)."""
+
+    @staticmethod
+    def forward(ctx, att, basis, d_pad):
+        lib = L.load()
+        att, basis = att.contiguous(), basis.contiguous()
+        (R, B), (_, rows, D) = att.shape, basis.shape
+        w = th.empty((R, rows, d_pad), dtype=th.float32, device=att.device)
+        L.check(lib.dg_basis_combine_fwd_f32(L.ptr(att, th.float32, 'att'), L.ptr(basis, th.float32, 'basis'), R, B, rows, D, d_pad,
+                                             L.ptr(w), L.stream()), 'basis_combine_fwd')
+        ctx.save_for_backward(att, basis)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        lib = L.load()
+        att, basis = ctx.saved_tensors
+        (R, B), (_, rows, D) = att.shape, basis.shape
+        dw = dw.contiguous()
+        dbasis = th.empty_like(basis)
+        datt = th.empty_like(att)
+        ws = L.workspace(lib.dg_basis_combine_bwd_workspace_bytes(rows, D), att.device)
+        L.check(lib.dg_basis_combine_bwd_f32(L.ptr(att), L.ptr(basis), L.ptr(dw, th.float32, 'dw'), R, B, rows, D, dw.shape[2],
+                                             L.ptr(dbasis), L.ptr(datt), L.ptr(ws), ws.numel(), L.stream()), 'basis_combine_bwd')
+        return datt, dbasis, None
+
+
+BASIS_MAX = 4
+
+
+def basis_combine(att, basis, mult=1):
+    """matmul(att [R, B], basis.view(B, -1)).view(R, in, D) zero-padded to a width that is a multiple of `mult`
+    ([R, in, Dp]); R, B <= 4 run as one elementwise kernel each way, anything larger as the reference's matmul + pad."""
+    if not att.is_cuda:
+        raise RuntimeError('dreamgnn_b200.basis_combine needs CUDA tensors (no CPU fallback)')
+    (R, B), (_, rows, D) = att.shape, basis.shape
+    d_pad = D + (-D) % max(int(mult), 1)
+    if R <= BASIS_MAX and B <= BASIS_MAX and att.dtype == th.float32 and basis.dtype == th.float32:
+        return BasisCombineFunction.apply(att, basis, d_pad)
+    w = th.matmul(att, basis.reshape(B, -1)).view(R, rows, D)
+    return th.nn.functional.pad(w, (0, d_pad - D)) if d_pad != D else w
+
+
+class WeightedLossSum(th.autograd.Function):
+    """total = rel + beta * (c1 + c2) (train.py:292-294) for three scalars: two launches forward, and the backward hands
+    the upstream gradient through and scales it once (autograd's trace of the expression: 3 + 5 scalar launches)."""
+
+    @staticmethod
+    def forward(ctx, rel, c1, c2, beta):
+        ctx.beta = float(beta)
+        return th.add(rel, c1 + c2, alpha=float(beta))
+
+    @staticmethod
+    def backward(ctx, g):
+        gb = g * ctx.beta
+        return g, gb, gb, None
 
 
 # ------------------------------------------------------------------------------------------------

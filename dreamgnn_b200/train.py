@@ -96,8 +96,11 @@ class TrainState:
         self.enc_graph, self.dec_graph, self.labels = enc_graph, dec_graph, labels
         self.drug_graph, self.dis_graph = drug_graph, dis_graph
         self.drug_feature_graph, self.disease_feature_graph = drug_feature_graph, disease_feature_graph
-        self.drug_feat, self.dis_feat = drug_feat, dis_feat
-        self.drug_sim_feat, self.dis_sim_feat = drug_sim_feat, dis_sim_feat
+        # row-major once, here: a Fortran-ordered array from loadmat keeps its strides through `x + noise`, and every
+        # GEMM of every iteration would then start with a contiguous copy of its input
+        dense = lambda t: t.contiguous() if isinstance(t, th.Tensor) and not t.is_sparse else t
+        self.drug_feat, self.dis_feat = dense(drug_feat), dense(dis_feat)
+        self.drug_sim_feat, self.dis_sim_feat = dense(drug_sim_feat), dense(dis_sim_feat)
 
 
 def augment_state(state, aug_methods, aug_params):
@@ -122,8 +125,23 @@ def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_param
         aug['enc_graph'], state.dec_graph, aug['drug_graph'], aug['drug_sim_feat'], aug['drug_feat'],
         aug['disease_graph'], aug['disease_sim_feat'], aug['disease_feat'], aug['drug_feature_graph'],
         aug['disease_feature_graph'], False)
-    rel = rel_loss_fn(pred.squeeze(-1), state.labels)
-    total = rel + beta * (common_loss_fn(drug_out, drug_sim_out) + common_loss_fn(dis_out, dis_sim_out))
+    ready = getattr(model, 'routes_ready', None)
+    if ready is not None:
+        # the common losses need only the route outputs: a side branch forked where those were complete, beside the
+        # attention + decoder + BCE (and, in the backward, beside the decoder's backward); joined for the total
+        main = th.cuda.current_stream()
+        side = th.cuda.Stream(device=main.device)
+        side.wait_event(ready)
+        with th.cuda.stream(side):
+            c_drug, c_dis = common_loss_fn(drug_out, drug_sim_out), common_loss_fn(dis_out, dis_sim_out)
+        rel = rel_loss_fn(pred.squeeze(-1), state.labels)
+        main.wait_stream(side)
+        c_drug.record_stream(main)
+        c_dis.record_stream(main)
+    else:
+        rel = rel_loss_fn(pred.squeeze(-1), state.labels)
+        c_drug, c_dis = common_loss_fn(drug_out, drug_sim_out), common_loss_fn(dis_out, dis_sim_out)
+    total = ops.WeightedLossSum.apply(rel, c_drug, c_dis, beta)
     optimizer.zero_grad()
     total.backward()
     clip_and_step(model, optimizer, grad_clip)

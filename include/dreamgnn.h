@@ -207,21 +207,26 @@ DG_API int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_
  * and, when y != NULL, y is written ([n_rows, d], leading dimension ldy; must not alias x). One pass over the matrix.
  * Replaces autograd's `grad.sum(0)` for the GraphConvolution / nn.Linear bias gradients (backward of layers.py:311-314,
  * layers.py:139-142) and the `grad * (out > 0)` of F.relu's backward (layers.py:247), and gives the column means of
- * utils.py:89-90. d % 4 == 0, rows 16-byte aligned. */
+ * utils.py:89-90. d % 4 == 0, rows 16-byte aligned.
+ * tickets (may be NULL): ceil(d / 128) device int32 that are ZERO on entry and zero again on completion, not shared with
+ * any call that may run concurrently. With them a matrix of <= 16 384 rows takes ONE launch (the CTA that finishes last
+ * adds the slab partials, in slab order: the result does not depend on which CTA that is) instead of two. */
 DG_API size_t dg_colsum_workspace_bytes(int64_t n_rows, int64_t d);
 DG_API int dg_colsum_f32(const float* x, int64_t ldx, const float* gate, int64_t ldg, float* y, int64_t ldy,
                          int64_t n_rows, int64_t d, float* out, void* workspace, size_t workspace_bytes,
-                         dg_stream_t stream);
+                         int32_t* tickets, dg_stream_t stream);
 /* Rows of common_loss (utils.py:87-95): z[i,:] = c_i / max(||c_i||_2, eps) with c_i = x[i,:] - colsum/n_rows, widened to
  * float64 (the Gram-matrix form of the loss accumulates in float64); inv_norm[i] = 1 / max(||c_i||, eps).
  * z is [n_rows, d] with leading dimension ldz (two embeddings are written side by side into one [n, 2d] operand). */
 DG_API int dg_center_normalize_f64(const float* x, int64_t ldx, const float* colsum, int64_t n_rows, int64_t d,
                                    double eps, double* z, int64_t ldz, double* inv_norm, dg_stream_t stream);
-/* Backward of the row normalisation: dc[i,:] = (gz[i,:] - z[i,:] * <z[i,:], gz[i,:]>) * inv_norm[i] (fp32 out); the
- * caller subtracts the column mean of dc afterwards (backward of the centring). */
+/* Backward of the row normalisation: dc[i,:] = (gz[i,:] - z[i,:] * <z[i,:], gz[i,:]>) * inv_norm[i] * s (fp32 out) with
+ * s = scale * (*gout) (gout: device float, the upstream scalar gradient; NULL = 1) -- the product is linear in gz, so the
+ * loss's constant factor and the upstream gradient need no pass of their own. The caller subtracts the column mean of dc
+ * afterwards (backward of the centring). */
 DG_API int dg_center_normalize_bwd_f64(const double* gz, int64_t ldgz, const double* z, int64_t ldz,
                                        const double* inv_norm, int64_t n_rows, int64_t d, float* dc, int64_t lddc,
-                                       dg_stream_t stream);
+                                       const float* gout, double scale, dg_stream_t stream);
 
 /* ---- kNN similarity graphs (data_loader.py:278-344, utils.py:11-27) ------------------------- */
 /* Per row of a float64 similarity block [n_rows, n_cols] (leading dimension ld), the k largest
@@ -277,6 +282,18 @@ DG_API int dg_bce_logits_bwd_f32(const float* logits, const float* target, int64
  * and -1 off them, and *loss (device float) = sum(G * gs) / n_rows^2 = (|G11|^2 + |G22|^2 - 2 |G12|^2) / n^2. One launch. */
 DG_API int dg_gram_common_loss_f64(const double* G, int64_t ldg, int64_t d, double n_rows, double* gs, float* loss,
                             dg_stream_t stream);
+
+/* Basis decomposition of the GCMC relation weights, W_r = sum_b att[r][b] * basis[b] (layers.py:120-121; the reference:
+ * matmul(att, basis.view(B, -1))): w [n_rel, rows, d_pad] with the columns [d, d_pad) zero (the aggregation kernels'
+ * width padding written in the same pass); att [n_rel, n_basis], basis [n_basis, rows, d] dense. n_rel, n_basis <= 4. */
+DG_API int dg_basis_combine_fwd_f32(const float* att, const float* basis, int n_rel, int n_basis, int64_t rows, int64_t d,
+                             int64_t d_pad, float* w, dg_stream_t stream);
+/* Its backward from dw [n_rel, rows, d_pad]: dbasis[b] = sum_r att[r][b] * dw[r] (dense [n_basis, rows, d]) and
+ * datt[r][b] = <dw[r], basis[b]> summed in float64 in a fixed order. Two launches. */
+DG_API size_t dg_basis_combine_bwd_workspace_bytes(int64_t rows, int64_t d);
+DG_API int dg_basis_combine_bwd_f32(const float* att, const float* basis, const float* dw, int n_rel, int n_basis, int64_t rows,
+                             int64_t d, int64_t d_pad, float* dbasis, float* datt, void* workspace, size_t workspace_bytes,
+                             dg_stream_t stream);
 
 /* nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step() (train.py:297-300) over a list of fp32
  * tensors in two launches per DG_ADAM_MAX_TENSORS_PER_LAUNCH tensors: the global gradient norm from per-chunk float64

@@ -206,3 +206,37 @@ def test_train_iteration_with_fused_tail_tracks_the_torch_tail(dev):
     a, b = np.array(curves[0]), np.array(curves[1])
     assert np.all(np.abs(a - b) <= 2e-5 * np.abs(a)), (a, b)
     assert b[-1] < b[0]
+
+
+# ---- basis decomposition of the relation weights ---------------------------------------------------
+@pytest.mark.parametrize('R,B,rows,D,mult', [(2, 2, 768, 341, 4), (2, 2, 128, 128, 4), (3, 2, 5, 7, 8), (4, 4, 33, 12, 32),
+                                             (5, 3, 9, 6, 4)])
+def test_basis_combine_matches_matmul(dev, R, B, rows, D, mult):
+    """layers.py:120-121: W = matmul(att, basis.view(B, -1)).view(R, in, msg), here at the padded message width, against
+    the same expression in float64 (value and both gradients); the padded columns are exactly zero."""
+    from dreamgnn_b200 import ops
+    gen = th.Generator(dev).manual_seed(R * 100 + D)
+    att = th.randn(R, B, generator=gen, device=dev).requires_grad_(True)
+    basis = th.randn(B, rows, D, generator=gen, device=dev).requires_grad_(True)
+    w = ops.basis_combine(att, basis, mult)
+    dp = D + (-D) % mult
+    assert w.shape == (R, rows, dp) and w.is_contiguous()
+    assert float(w[:, :, D:].abs().sum()) == 0.0
+    att64, basis64 = att.detach().double().requires_grad_(True), basis.detach().double().requires_grad_(True)
+    ref = th.matmul(att64, basis64.view(B, -1)).view(R, rows, D)
+    assert H.rel_err(w[:, :, :D], ref) <= 1e-6
+    g = th.randn(R, rows, dp, generator=gen, device=dev)
+    w.backward(g)
+    ref.backward(g[:, :, :D].double())
+    assert H.rel_err(att.grad, att64.grad) <= 2e-6
+    assert H.rel_err(basis.grad, basis64.grad) <= 1e-6
+
+
+def test_weighted_loss_sum(dev):
+    from dreamgnn_b200 import ops
+    for device in (dev, th.device('cpu')):
+        xs = [th.tensor(v, device=device, requires_grad=True) for v in (0.7, 2.5, -1.25)]
+        total = ops.WeightedLossSum.apply(xs[0], xs[1], xs[2], 0.001)
+        assert abs(float(total) - (0.7 + 0.001 * (2.5 - 1.25))) < 1e-7
+        (total * 2.0).backward()
+        assert [round(float(x.grad), 7) for x in xs] == [2.0, 0.002, 0.002]
