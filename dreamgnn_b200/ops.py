@@ -290,13 +290,21 @@ def _rows_ok(t):
 def colsum(x, gate=None, want_masked=False):
     """Deterministic x.sum(0) of a [n, d] fp32 matrix in one pass; with `gate` the sum (and, if `want_masked`,
     the returned matrix) is of x * (gate > 0) -- F.relu's backward fused with the bias gradient.
-    Returns sum [d] or (masked [n, d], sum [d]). Shapes the kernel cannot address (d % 4 != 0, unaligned rows)
-    take the equivalent torch expression on the device."""
+    Returns sum [d] or (masked [n, d], sum [d]). Shapes the kernel cannot address directly (d % 4 != 0, unaligned rows)
+    go through zero-padded aligned copies."""
     if not x.is_cuda:
         raise RuntimeError('dreamgnn_b200.colsum needs CUDA tensors (no CPU fallback)')
-    if not (x.dim() == 2 and x.shape[0] > 0 and _rows_ok(x) and (gate is None or (_rows_ok(gate) and gate.shape == x.shape))):
-        y = x if gate is None else x * (gate > 0).to(x.dtype)
-        return (y, y.sum(0)) if want_masked else y.sum(0)
+    if x.dim() != 2 or x.dtype != th.float32 or (gate is not None and gate.shape != x.shape):
+        raise ValueError('colsum: a 2-D fp32 matrix (and a gate of the same shape) expected')
+    if x.shape[0] == 0:
+        return (x, x.new_zeros(x.shape[1])) if want_masked else x.new_zeros(x.shape[1])
+    if not (_rows_ok(x) and (gate is None or _rows_ok(gate))):
+        # rows the float4 kernel cannot address (width not a multiple of 4, unaligned or strided rows): the same kernel
+        # on zero-padded aligned copies -- never a library reduction
+        d0 = x.shape[1]
+        aligned = lambda t: th.nn.functional.pad(t, (0, (-d0) % 4)).contiguous()
+        res = colsum(aligned(x), None if gate is None else aligned(gate), want_masked)
+        return (res[0][:, :d0], res[1][:d0]) if want_masked else res[:d0]
     lib = L.load()
     n, d = x.shape
     out = th.empty(d, dtype=th.float32, device=x.device)
@@ -569,15 +577,21 @@ class ActDropoutFunction(th.autograd.Function):
 
 def act_dropout(x, act=None, slope=0.1, p=0.0, training=True, seed=None):
     """dropout(act(x)) for a 2-D fp32 CUDA matrix, act in {None, 'leaky', 'relu'} (layers.py:134-138, 247, 281-282).
-    Rows that the float4 kernel cannot address (width not a multiple of 4, unaligned) take the same expression in torch."""
+    Rows that the float4 kernel cannot address (width not a multiple of 4, unaligned) go through a zero-padded copy."""
     if not x.is_cuda:
         raise RuntimeError('dreamgnn_b200.act_dropout needs CUDA tensors (no CPU fallback)')
     p = float(p) if training else 0.0
     if act in (None, 'identity') and p == 0.0:
         return x
-    if not (x.dim() == 2 and x.shape[0] > 0 and _rows_ok(x)):
-        y = x if act in (None, 'identity') else (th.nn.functional.leaky_relu(x, slope) if act == 'leaky' else th.relu(x))
-        return th.nn.functional.dropout(y, p, True) if p > 0 else y
+    if x.dim() != 2 or x.dtype != th.float32:
+        raise ValueError('act_dropout: a 2-D fp32 matrix expected')
+    if x.shape[0] == 0:
+        return x
+    if not _rows_ok(x):
+        # rows the float4 kernel cannot address: the same kernel on a zero-padded aligned copy (act(0) = 0 for all three)
+        d0 = x.shape[1]
+        xp = th.nn.functional.pad(x, (0, (-d0) % 4)).contiguous()
+        return act_dropout(xp, act, slope, p, True, seed)[:, :d0]
     if seed is None:
         seed = fresh_seed(x.device) if p > 0 else 0
     return ActDropoutFunction.apply(x, ACT_CODES[act], slope, p, seed)

@@ -446,7 +446,7 @@ def test_colsum_is_deterministic_and_exact(dev, n, d, gated):
     assert err <= 1e-6 * max(1.0, want_m.abs().sum(0).max().item() if n else 1.0)
     s2 = ops().colsum(xs, gate=gs)
     assert th.equal(s, s2)                                                    # fixed summation order: bit-identical
-    # a strided view (rows 16-byte aligned) goes through the kernel too; an unaligned one takes the torch expression
+    # a strided view (rows 16-byte aligned) goes through the kernel as it is, an unaligned one through an aligned copy
     if d >= 8 and n:
         v = xs[:, 4:d]
         np.testing.assert_allclose(ops().colsum(v).cpu().numpy(), x[:, 4:d].double().sum(0).numpy(), rtol=0, atol=1e-3)

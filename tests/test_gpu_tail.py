@@ -240,3 +240,39 @@ def test_weighted_loss_sum(dev):
         assert abs(float(total) - (0.7 + 0.001 * (2.5 - 1.25))) < 1e-7
         (total * 2.0).backward()
         assert [round(float(x.grad), 7) for x in xs] == [2.0, 0.002, 0.002]
+
+
+def test_cuda_graph_iteration_with_fused_tail(dev):
+    """The captured iteration with the fused loss / clip / Adam (what train() --cuda_graph and bench.py run): replays draw
+    fresh seeds from the per-iteration pool, the step counter and moments advance on the device, and the loss falls to the
+    level of the eager loop with torch's own tail."""
+    import argparse as ap
+    from dreamgnn_b200 import ops, synthetic
+    from dreamgnn_b200.graphed import GraphedIteration
+    from dreamgnn_b200.model import Net
+    from dreamgnn_b200.optim import FusedAdam
+    from dreamgnn_b200.train import aug_params_from_args, train_iteration
+    from dreamgnn_b200.utils import common_loss
+    spec = dict(kind='dense', n_drug=90, n_dis=70, n_pos=400, f_drug=48, f_dis=48, k=4)
+    w = synthetic.make_workload(spec, dev, seed=5)
+    state = synthetic.train_state(w, dev)
+    margs = synthetic.model_args(w, gcn_agg_units=96, gcn_out_units=16, nhid1=40, nhid2=16)
+    side = th.cuda.Stream()
+    with th.cuda.stream(side):
+        th.manual_seed(9)
+        model = Net(margs).to(dev)
+        opt = FusedAdam(model.parameters(), lr=0.002, weight_decay=1e-5)
+        step = GraphedIteration(model, opt, state, rel_loss_fn=ops.FusedBCEWithLogitsLoss())
+        first = float(opt.state[next(iter(model.parameters()))]['step'])
+        graphed = [float(step().detach()) for _ in range(40)]
+        assert float(opt.state[next(iter(model.parameters()))]['step']) == first + 40
+        th.manual_seed(9)
+        ref_model = Net(margs).to(dev)
+        ref_opt = th.optim.Adam(ref_model.parameters(), lr=0.002, weight_decay=1e-5)
+        p = aug_params_from_args(ap.Namespace())
+        eager = [float(train_iteration(ref_model, ref_opt, state, th.nn.BCEWithLogitsLoss(), ['edge_dropout', 'feature_noise'], p,
+                                       0.001, 1.0, common_loss).detach()) for _ in range(40 + step.eager_iterations)]
+    th.cuda.current_stream().wait_stream(side)
+    assert all(np.isfinite(graphed)) and np.mean(graphed[-10:]) < np.mean(graphed[:10])
+    assert len({round(x, 6) for x in graphed[:5]}) == 5                # replays are not identical: fresh random draws
+    assert abs(np.mean(graphed[-10:]) - np.mean(eager[-10:])) < 0.05
