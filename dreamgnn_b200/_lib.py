@@ -50,6 +50,10 @@ _SIGNATURES = {
                                c_int64, _P, c_int, _P, c_size_t, _P]),
     'dg_gemm_f32': (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int64, c_int64,
                             c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
+    'dg_small_gemm_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
+    'dg_small_gemm_tickets': (c_int64, [c_int64, c_int64, c_int64, c_int64]),
+    'dg_small_gemm_f32': (c_int, [_P, c_int64, c_int64, c_int, _P, c_int64, c_int64, c_int, _P, _P, c_int64, c_int64, c_int64,
+                                  c_int64, c_int64, c_int64, c_int, _P, c_size_t, _P, _P]),
     'dg_colsum_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'dg_colsum_f32': (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P, _P]),
     'dg_center_normalize_f64': (c_int, [_P, c_int64, _P, c_int64, c_int64, c_double, _P, c_int64, _P, _P]),

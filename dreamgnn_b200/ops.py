@@ -268,7 +268,7 @@ _TICKET_SLOTS = 8192
 
 def _tickets(device, count):
     """Device address of `count` zeroed tickets (None when the request is larger than a slot run)."""
-    if count > 64:
+    if count > _TICKET_SLOTS // 4:
         return None
     pool = _TICKET_POOL.get(device)
     if pool is None or (pool[2] != th.cuda.is_current_stream_capturing() and pool[2]):
@@ -951,7 +951,7 @@ def knn_graph_from_neighbors(nbr):
 # ------------------------------------------------------------------------------------------------
 import os as _os
 
-GEMM_MIN_MACS = int(_os.environ.get('DG_GEMM_MIN_MACS', str(1 << 26)))   # below this: cuBLAS via torch (launch + operand split cost)
+GEMM_MIN_MACS = int(_os.environ.get('DG_GEMM_MIN_MACS', str(1 << 26)))   # below this: the one-launch fp32 small_gemm (the tcgen05 kernel has a ~20 us floor)
 
 
 def gemm_backend():
@@ -1038,44 +1038,102 @@ class LinearFunction(th.autograd.Function):
         return dx, dw, db
 
 
-class SmallLinearFunction(th.autograd.Function):
-    """y = x @ w^T + b below the tensor-core kernel's size threshold: the three GEMMs stay with the library (cuBLAS via
-    torch), the bias gradient is the deterministic one-pass column sum (autograd's dy.sum(0) is a single-CTA reduction
-    at these shapes: ~30 us on the critical path of every small layer)."""
+SMALL_GEMM = _os.environ.get('DG_SMALL_GEMM', '1') != '0'      # 0: the library (torch / cuBLAS) for the small layers, for A/B runs
+
+
+def small_gemm(a, b, trans_a=False, trans_b=False, bias=None, reduce_batch=False):
+    """C[r] = op(A[r]) @ op(B[r])^T (+ bias) in plain fp32 for the small dense layers (csrc/small_gemm.cu): same operand
+    conventions as `gemm` (a: [M,K] or [K,M] with trans_a; b: [N,K] or [K,N] with trans_b; 3-D = batched, a 2-D operand is
+    shared), any row stride, one launch (split-K and, with reduce_batch, the sum over the batch are added in the kernel)."""
+    lib = L.load()
+    if not (a.is_cuda and b.is_cuda):
+        raise RuntimeError('dreamgnn_b200.small_gemm needs CUDA tensors (no CPU fallback)')
+    if a.dtype != th.float32 or b.dtype != th.float32:
+        raise TypeError('small_gemm: fp32 operands expected')
+    rows_ok = lambda t: t.stride(-1) == 1 and t.stride(-2) >= t.shape[-1]          # any row stride; no broadcast views
+    a = a if rows_ok(a) else a.contiguous()
+    b = b if rows_ok(b) else b.contiguous()
+    batch = max(a.shape[0] if a.dim() == 3 else 1, b.shape[0] if b.dim() == 3 else 1)
+    (K, M) = a.shape[-2:] if trans_a else a.shape[-2:][::-1]
+    (Kb, N) = b.shape[-2:] if trans_b else b.shape[-2:][::-1]
+    if Kb != K:
+        raise ValueError('small_gemm: inner dimensions differ (%d vs %d)' % (K, Kb))
+    sa = a.stride(0) if (a.dim() == 3 and batch > 1 and a.shape[0] > 1) else 0
+    sb = b.stride(0) if (b.dim() == 3 and batch > 1 and b.shape[0] > 1) else 0
+    batched_out = (a.dim() == 3 or b.dim() == 3) and not reduce_batch
+    out = th.empty((batch, M, N) if batched_out else (M, N), dtype=th.float32, device=a.device)
+    if bias is not None:
+        bias = bias.reshape(-1).to(th.float32).contiguous()
+        if bias.numel() != N:
+            raise ValueError('small_gemm: bias must have N elements')
+    ws = L.workspace(lib.dg_small_gemm_workspace_bytes(M, N, K, batch), a.device)
+    n_tk = int(lib.dg_small_gemm_tickets(M, N, K, batch))
+    tk = _tickets(a.device, n_tk) if n_tk else None
+    L.check(lib.dg_small_gemm_f32(a.data_ptr(), a.stride(-2), sa, int(trans_a), b.data_ptr(), b.stride(-2), sb, int(trans_b),
+                                  L.ptr(bias), L.ptr(out), N, M * N, M, N, K, batch, int(bool(reduce_batch)), L.ptr(ws), ws.numel(),
+                                  tk, L.stream()), 'small_gemm')
+    return out
+
+
+class SmallProjectFunction(th.autograd.Function):
+    """y[r] = x @ w[r] for the R relation weights at once below the tensor-core kernel's size threshold: one small_gemm launch
+    each for y, dx (summed over the relations inside the kernel) and dw."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        return th.addmm(b, x, w.t())
+        return small_gemm(x, w, trans_b=True)                                    # w[r] is [K, N] as stored
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        dy = dy.contiguous()
-        dx = dy @ w if ctx.needs_input_grad[0] else None
-        dw = dy.t() @ x if ctx.needs_input_grad[1] else None
-        db = colsum(dy) if ctx.needs_input_grad[2] else None
+        dy = dy if dy.stride(-1) == 1 else dy.contiguous()
+        dx = small_gemm(dy, w, reduce_batch=True) if ctx.needs_input_grad[0] else None         # sum_r dy[r] @ w[r]^T
+        dw = small_gemm(x, dy, trans_a=True, trans_b=True) if ctx.needs_input_grad[1] else None  # x^T @ dy[r]
+        return dx, dw
+
+
+class SmallLinearFunction(th.autograd.Function):
+    """y = x @ w^T + b below the tensor-core kernel's size threshold: one small_gemm launch each for y (bias in the
+    epilogue), dx and dw (split-K added inside the kernel); the bias gradient is the deterministic one-pass column sum.
+    (The library: SIMT sgemm + bias epilogue launch forward, sgemm + split-K reduction launches backward.)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return small_gemm(x, w, bias=b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy if dy.stride(-1) == 1 else dy.contiguous()
+        dx = small_gemm(dy, w, trans_b=True) if ctx.needs_input_grad[0] else None
+        dw = small_gemm(dy, x, trans_a=True, trans_b=True) if ctx.needs_input_grad[1] else None
+        db = colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 
 
 def linear(x, w, b=None):
-    """F.linear(x, w, b) for 2-D x; tcgen05 3xTF32 above GEMM_MIN_MACS, cuBLAS (torch) below."""
+    """F.linear(x, w, b) for 2-D x; tcgen05 3xTF32 above GEMM_MIN_MACS, the one-launch fp32 small_gemm below."""
     if not x.is_cuda:
         raise RuntimeError('dreamgnn_b200.linear needs CUDA tensors (no CPU fallback)')
     if (gemm_backend() == 'tcgen05' and x.dim() == 2 and x.dtype == th.float32 and w.dtype == th.float32
             and x.shape[0] * w.shape[0] * w.shape[1] >= GEMM_MIN_MACS):
         return LinearFunction.apply(x, w, b)
-    if b is not None and x.dim() == 2 and x.dtype == th.float32 and w.dtype == th.float32 and w.shape[0] % 4 == 0:
+    if x.dim() == 2 and x.dtype == th.float32 and w.dtype == th.float32 and gemm_backend() != 'cublas' and SMALL_GEMM:
         return SmallLinearFunction.apply(x, w, b)
-    return th.nn.functional.linear(x, w, b)
+    return th.nn.functional.linear(x, w, b)                    # DG_GEMM=cublas (A/B runs), or not a 2-D fp32 product
 
 
 def project(x, w):
-    """x [M,K] @ w [R,K,N] -> [R,M,N]; tcgen05 3xTF32 for the large projections, cuBLAS below GEMM_MIN_MACS."""
+    """x [M,K] @ w [R,K,N] -> [R,M,N]; tcgen05 3xTF32 for the large projections, the fp32 small_gemm below GEMM_MIN_MACS."""
     if not x.is_cuda:
         raise RuntimeError('dreamgnn_b200.project needs CUDA tensors (no CPU fallback)')
     R, K, N = w.shape
     macs = x.shape[0] * K * N * R
     if gemm_backend() == 'tcgen05' and x.dtype == th.float32 and macs >= GEMM_MIN_MACS:
         return ProjectFunction.apply(x, w)
+    if gemm_backend() != 'cublas' and SMALL_GEMM and x.dtype == th.float32 and w.dtype == th.float32 and x.dim() == 2:
+        return SmallProjectFunction.apply(x, w)
     return th.matmul(x.unsqueeze(0), w)

@@ -200,6 +200,22 @@ DG_API int dg_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_
                        int64_t K, int64_t batch, const float* row_scale, int precision, void* workspace,
                        size_t workspace_bytes, dg_stream_t stream);
 
+/* fp32 GEMM for the small dense layers of the real-dataset shapes (csrc/small_gemm.cu): C[b] = op(A[b]) . op(B[b])^T (+ bias
+ * [N]), same operand conventions as dg_gemm_f32 (op(A) [M, K], op(B) [N, K]; trans_x: stored [K, M] / [K, N]; stride 0 = an
+ * operand shared by the batch), but plain fp32 FMAs in ascending k, no alignment requirement, ONE launch. reduce_batch != 0
+ * sums over the batch into a single C [M, N] (the batch is walked inside the k-loop). Very long K with few output tiles is
+ * split over CTAs and the partial tiles are added inside the kernel by the last CTA of each tile in split order
+ * (deterministic). Replaces th.addmm / th.matmul (cuBLAS SIMT sgemm + split-K reduction + bias epilogue launches) behind
+ * nn.Linear at layers.py:139-142, 281-282, 366-369 and the 128 -> 128 projections of layers.py:220-221.
+ * tickets: dg_small_gemm_tickets(M, N, K, batch) device int32 (0 = none needed: NULL is fine), ZERO on entry and zero again
+ * on completion, not shared with a call that may run concurrently. */
+DG_API size_t dg_small_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch);
+DG_API int64_t dg_small_gemm_tickets(int64_t M, int64_t N, int64_t K, int64_t batch);
+DG_API int dg_small_gemm_f32(const float* A, int64_t lda, int64_t stride_a, int trans_a, const float* B, int64_t ldb,
+                      int64_t stride_b, int trans_b, const float* bias, float* C, int64_t ldc, int64_t stride_c, int64_t M,
+                      int64_t N, int64_t K, int64_t batch, int reduce_batch, void* workspace, size_t workspace_bytes,
+                      int32_t* tickets, dg_stream_t stream);
+
 /* ---- row-streaming helpers around the aggregation kernels ------------------------------------ */
 /* Deterministic column sums of a row-major fp32 matrix (fixed slab partition, fixed summation order, no atomics):
  *   out[j] = sum_i y[i][j],  y = x            (gate == NULL)

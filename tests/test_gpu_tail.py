@@ -276,3 +276,64 @@ def test_cuda_graph_iteration_with_fused_tail(dev):
     assert all(np.isfinite(graphed)) and np.mean(graphed[-10:]) < np.mean(graphed[:10])
     assert len({round(x, 6) for x in graphed[:5]}) == 5                # replays are not identical: fresh random draws
     assert abs(np.mean(graphed[-10:]) - np.mean(eager[-10:])) < 0.05
+
+
+# ---- small fp32 GEMM ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (7, 5, 3), (64, 64, 16), (65, 63, 17), (763, 128, 344), (128, 344, 763), (681, 128, 128),
+                                   (128, 128, 5000), (3, 200, 700)])
+@pytest.mark.parametrize('ta', [False, True])
+@pytest.mark.parametrize('tb', [False, True])
+def test_small_gemm_all_layouts(dev, M, N, K, ta, tb):
+    from dreamgnn_b200 import ops
+    gen = th.Generator(dev).manual_seed(M * 7 + N * 3 + K)
+    a = th.randn((K, M) if ta else (M, K), generator=gen, device=dev)
+    b = th.randn((K, N) if tb else (N, K), generator=gen, device=dev)
+    bias = th.randn(N, generator=gen, device=dev)
+    want = (a.double().t() if ta else a.double()) @ (b.double() if tb else b.double().t())
+    c = ops.small_gemm(a, b, ta, tb)
+    assert c.shape == (M, N) and H.rel_err(c, want) <= 2e-6
+    assert th.equal(c, ops.small_gemm(a, b, ta, tb))                  # split-K parts are added in split order: bit-identical
+    assert H.rel_err(ops.small_gemm(a, b, ta, tb, bias=bias), want + bias.double()) <= 2e-6
+    # row-strided views are read as stored
+    wide = th.randn(a.shape[0], a.shape[1] + 5, generator=gen, device=dev)
+    wide[:, 2:2 + a.shape[1]] = a
+    assert th.equal(ops.small_gemm(wide[:, 2:2 + a.shape[1]], b, ta, tb), c)
+
+
+@pytest.mark.parametrize('R,M,N,K', [(2, 763, 128, 128), (2, 90, 16, 16), (3, 257, 65, 300), (4, 5, 3, 2)])
+def test_small_gemm_batched_and_reduced(dev, R, M, N, K):
+    from dreamgnn_b200 import ops
+    gen = th.Generator(dev).manual_seed(R + M + N + K)
+    x = th.randn(M, K, generator=gen, device=dev)
+    w = th.randn(R, K, N, generator=gen, device=dev)
+    y = ops.small_gemm(x, w, trans_b=True)                             # shared A, batched B stored [K, N]
+    assert y.shape == (R, M, N) and H.rel_err(y, th.matmul(x.double().unsqueeze(0), w.double())) <= 2e-6
+    dy = th.randn(R, M, N, generator=gen, device=dev)
+    dx = ops.small_gemm(dy, w, reduce_batch=True)                      # sum_r dy[r] @ w[r]^T
+    assert dx.shape == (M, K) and H.rel_err(dx, th.einsum('rmn,rkn->mk', dy.double(), w.double())) <= 2e-6
+    assert th.equal(dx, ops.small_gemm(dy, w, reduce_batch=True))
+    dw = ops.small_gemm(x, dy, trans_a=True, trans_b=True)             # x^T @ dy[r]
+    assert dw.shape == (R, K, N) and H.rel_err(dw, th.einsum('mk,rmn->rkn', x.double(), dy.double())) <= 2e-6
+
+
+@pytest.mark.parametrize('M,K,N,R', [(763, 344, 128, 2), (90, 35, 16, 2), (681, 128, 128, 2)])
+def test_small_linear_and_project_autograd(dev, M, K, N, R):
+    """ops.linear / ops.project below the tensor-core threshold (the real-dataset layers) against torch in float64:
+    value and every gradient."""
+    from dreamgnn_b200 import ops
+    gen = th.Generator(dev).manual_seed(M + K + N)
+    x = th.randn(M, K, generator=gen, device=dev).requires_grad_(True)
+    w = (th.randn(N, K, generator=gen, device=dev) / K ** 0.5).requires_grad_(True)
+    b = th.randn(N, generator=gen, device=dev).requires_grad_(True)
+    wr = (th.randn(R, K, N, generator=gen, device=dev) / K ** 0.5).requires_grad_(True)
+    assert M * K * N < ops.GEMM_MIN_MACS
+    y, h = ops.linear(x, w, b), ops.project(x, wr)
+    x64, w64, b64, wr64 = (t.detach().double().requires_grad_(True) for t in (x, w, b, wr))
+    y64, h64 = th.nn.functional.linear(x64, w64, b64), th.matmul(x64.unsqueeze(0), wr64)
+    assert H.rel_err(y, y64) <= 2e-6 and H.rel_err(h, h64) <= 2e-6
+    gy, gh = th.randn(M, N, generator=gen, device=dev), th.randn(R, M, N, generator=gen, device=dev)
+    ((y * gy).sum() + (h * gh).sum()).backward()
+    ((y64 * gy.double()).sum() + (h64 * gh.double()).sum()).backward()
+    for got, want in ((x.grad, x64.grad), (w.grad, w64.grad), (b.grad, b64.grad), (wr.grad, wr64.grad)):
+        assert H.rel_err(got, want) <= 3e-6
+    assert H.rel_err(ops.linear(x.detach(), w.detach()), th.nn.functional.linear(x64, w64)) <= 2e-6      # no bias
