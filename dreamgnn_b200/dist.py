@@ -440,10 +440,20 @@ class GraphedPartitionedIteration:
     The optimizer must be capturable (`torch.optim.Adam(..., capturable=True)`) and the model must not have run on the
     legacy default stream (make a side stream current first, as bench.py does)."""
 
-    def __init__(self, model, optimizer, state, warmup=3, **step_kwargs):
+    def __init__(self, model, optimizer, state, warmup=3, parallel_branches=None, **step_kwargs):
         if not all(g.get('capturable', False) for g in optimizer.param_groups):
             raise ValueError('the optimizer must be built with capturable=True')
         self._step = lambda: train_iteration_partitioned(model, optimizer, state, **step_kwargs)
+        # The two node types (and the GCMC / FGCN routes) as parallel stream branches of the graph: every collective blocks
+        # only the branch that needs it, so an all-gather (forward) or reduce-scatter (backward: autograd replays each node
+        # on its forward stream) of one branch runs under the other branch's projection / SpMM. The issue order of the
+        # collectives is the host order of the branches -- the same on every rank.
+        if parallel_branches is None:
+            import os
+            parallel_branches = os.environ.get('DG_ROWS_BRANCHES', '1') != '0'
+        self.parallel_branches = bool(parallel_branches) and hasattr(model, 'parallel_routes')
+        if self.parallel_branches:
+            model.parallel_routes = True
         side = th.cuda.Stream()
         side.wait_stream(th.cuda.current_stream())
         with th.cuda.stream(side):                       # eager warm-up: cached transposes, NCCL communicators, cuBLAS handles
@@ -458,6 +468,8 @@ class GraphedPartitionedIteration:
         with th.cuda.graph(self.graph, capture_error_mode='thread_local'):
             self.loss = self._step()
         ops.drop_seed_pool()                               # its buffer now belongs to the graph
+        if self.parallel_branches:
+            model.parallel_routes = False                  # the branches are in the graph; eager calls stay serial
         th.cuda.synchronize()
 
     def __call__(self):

@@ -308,8 +308,19 @@ class GCMCLayer(nn.Module):
         missing = [t for t in ('drug', 'disease') if t not in seen]
         if missing:
             raise KeyError('no relation into node type %r' % missing[0])
+        def aggregate_one_partitioned(dst_type):
+            """Row-partitioned graph, one node type on its own stream branch: exchange, then aggregate. The collectives of
+            this branch (forward all-gather, backward reduce-scatter: blocking on ITS stream) overlap the other branch's
+            projection / SpMM in both directions."""
+            from . import dist as _dist
+            blk, x, wstack, scale = messages(dst_type)
+            buf, src_scale, finish = _dist.gcmc_exchange(x, wstack, scale)
+            ci = _flat_f32(graph.nodes[dst_type].data['ci'])
+            return ops.spmm(blk.csr, finish(buf), src_scale=src_scale, dst_scale=ci, tag='gcmc')
+
         if ops.PARALLEL_BRANCHES:                                  # the two node types as parallel stream branches
-            drug, dis = ops.branches([lambda: tail('drug', aggregate('drug')), lambda: tail('disease', aggregate('disease'))])
+            one = aggregate if part is None else aggregate_one_partitioned
+            drug, dis = ops.branches([lambda: tail('drug', one('drug')), lambda: tail('disease', one('disease'))])
             return drug, dis
         # serial: the reference's dropout draw order (cj per etype in canonical order, then drug, then disease)
         aggs = aggregate_partitioned() if part is not None else {t: aggregate(t) for t in seen}
