@@ -24,6 +24,7 @@ FAMILIES = {
     'sass_decoder_tc.txt': ('decoder_', 'fused pair-gather + MLP decoder (csrc/decoder_tc.cu, csrc/decoder.cu)'),
     'sass_spmm.txt': ('spmm_', 'CSR SpMM (csrc/spmm.cu)'),
     'sass_rowops.txt': ('colsum|center_normalize|attention|leaky|bce', 'row-streaming kernels (csrc/rowops.cu, csrc/fused.cu)'),
+    'sass_tail.txt': ('small_gemm|adam_|bce_|gram_loss|basis_', 'small fp32 GEMM and the loss / optimiser tail (csrc/small_gemm.cu, loss.cu, optim.cu, basis.cu)'),
 }
 
 
