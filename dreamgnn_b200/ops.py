@@ -267,14 +267,16 @@ _TICKET_SLOTS = 8192
 
 
 def _tickets(device, count):
-    """Device address of `count` zeroed tickets (None when the request is larger than a slot run)."""
+    """Device address of `count` zeroed tickets, or None (the caller then takes its two-launch form) when the request is
+    larger than the pool serves or when the pool would have to be created inside a CUDA-graph capture -- it must outlive
+    every graph, so it is only ever allocated eagerly (every capture in this package follows an eager warm-up)."""
     if count > _TICKET_SLOTS // 4:
         return None
     pool = _TICKET_POOL.get(device)
-    if pool is None or (pool[2] != th.cuda.is_current_stream_capturing() and pool[2]):
-        # (a pool first allocated during a graph capture lives in that graph's memory: make a fresh one outside it)
-        buf = th.zeros(_TICKET_SLOTS, dtype=th.int32, device=device)
-        pool = _TICKET_POOL[device] = [buf, 0, th.cuda.is_current_stream_capturing()]
+    if pool is None:
+        if th.cuda.is_current_stream_capturing():
+            return None
+        pool = _TICKET_POOL[device] = [th.zeros(_TICKET_SLOTS, dtype=th.int32, device=device), 0]
     if pool[1] + count > _TICKET_SLOTS:
         pool[1] = 0
     addr = pool[0].data_ptr() + 4 * pool[1]
@@ -1069,6 +1071,9 @@ def small_gemm(a, b, trans_a=False, trans_b=False, bias=None, reduce_batch=False
     ws = L.workspace(lib.dg_small_gemm_workspace_bytes(M, N, K, batch), a.device)
     n_tk = int(lib.dg_small_gemm_tickets(M, N, K, batch))
     tk = _tickets(a.device, n_tk) if n_tk else None
+    if n_tk and tk is None:
+        raise RuntimeError('small_gemm: a split-K product (K >= 2048 with few output tiles) needs the ticket pool, which is only '
+                           'allocated outside CUDA-graph capture: run the step once eagerly before capturing it')
     L.check(lib.dg_small_gemm_f32(a.data_ptr(), a.stride(-2), sa, int(trans_a), b.data_ptr(), b.stride(-2), sb, int(trans_b),
                                   L.ptr(bias), L.ptr(out), N, M * N, M, N, K, batch, int(bool(reduce_batch)), L.ptr(ws), ws.numel(),
                                   tk, L.stream()), 'small_gemm')
