@@ -44,15 +44,44 @@ PIPELINE_MAX_PAIRS = 4_000_000     # above this the iteration is bandwidth-bound
 
 
 # ---- structural clone / in-place refresh of an augmentation result -----------------------------------
+class _Arena:
+    """Bump allocator over ONE device buffer. Two arenas filled by the same sequence of requests have identical layouts,
+    so a whole tree of tensors living in one arena is copied into its twin with a single device-to-device copy (the
+    `live <- staged` step every replay starts with: ~60 tensors = ~60 serial copy nodes at the head of the graph before)."""
+    ALIGN = 256
+
+    def __init__(self, nbytes, device):
+        self.buf = th.empty(max(int(nbytes), 1), dtype=th.uint8, device=device)
+        self.off = 0
+
+    @classmethod
+    def span(cls, t):
+        return (t.numel() * t.element_size() + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+
+    def view_like(self, t):
+        """An uninitialised contiguous tensor of t's dtype and shape inside the arena."""
+        n = t.numel() * t.element_size()
+        if self.off + n > self.buf.numel():
+            raise ValueError('arena too small')
+        v = self.buf[self.off:self.off + n].view(t.dtype).view(t.shape)
+        self.off += self.span(t)
+        return v
+
+    def take_like(self, t):
+        """...holding a copy of t."""
+        v = self.view_like(t)
+        v.copy_(t)
+        return v
+
+
 def _csr_pair(c):
     """The CSR and (if present) its cached transpose, each once."""
     return [c] if c._t is None else [c, c._t]
 
 
-def _clone_csr(c):
+def _clone_csr(c, take):
     def one(x):
-        n = ops.CSR(x.indptr.clone(), x.indices.clone(), x.eid.clone(), None if x.vals is None else x.vals.clone(),
-                    x.n_rows, x.n_cols)
+        n = ops.CSR(take(x.indptr), take(x.indices), take(x.eid), None if x.vals is None else take(x.vals), x.n_rows, x.n_cols)
         n.slot_order, n.eid_is_slot, n.parent_nnz = x.slot_order, x.eid_is_slot, x.parent_nnz
         return n
     n = one(c)
@@ -69,29 +98,30 @@ def _csr_tensors(c):
     return out
 
 
-def _clone_entry(v):
-    """Deep copy of one value of an augmentation dict: dense tensor, sparse-COO adjacency with its CSR
-    sidecar, or a dropped HeteroGraph (relation blocks prebuilt). Anything else cannot be staged."""
+def _clone_entry(v, take):
+    """Deep copy of one value of an augmentation dict -- dense tensor, sparse-COO adjacency with its CSR sidecar, or a
+    dropped HeteroGraph (relation blocks prebuilt) -- with every tensor obtained from `take(source)` in the order
+    `_entry_tensors` lists them. Anything else cannot be staged."""
     if isinstance(v, th.Tensor) and v.is_sparse:
         csr = getattr(v, '_dg_csr', None)
         if csr is None:
             raise ValueError('sparse adjacency without a CSR sidecar')
-        t = th.sparse_coo_tensor(v._indices().clone(), v._values().clone(), v.shape, device=v.device,
-                                 check_invariants=False)
-        t._dg_csr = _clone_csr(csr)
+        t = th.sparse_coo_tensor(take(v._indices()), take(v._values()), v.shape, device=v.device, check_invariants=False)
+        t._dg_csr = _clone_csr(csr, take)
         return t
     if isinstance(v, th.Tensor):
-        return v.clone()
+        return take(v)
     if isinstance(v, HeteroGraph):
         if not v._blocks or any(not isinstance(e, _LazyEdges) for e in v._edges.values()):
             raise ValueError('only edge-dropped graphs (prebuilt relation blocks) can be staged')
         blocks, lazy = {}, {}
-        for dt, b in v._blocks.items():
-            nb = RelBlock(b.etypes, b.src_type, b.dst_type, b.n_src, b.n_dst, _clone_csr(b.csr), b.offsets)
+        for dt in sorted(v._blocks):
+            b = v._blocks[dt]
+            nb = RelBlock(b.etypes, b.src_type, b.dst_type, b.n_src, b.n_dst, _clone_csr(b.csr, take), b.offsets)
             blocks[dt] = nb
             for r, c in enumerate(b.etypes):
                 lazy[c] = _LazyEdges(nb, r, v._edges[c].count, v.idtype)
-        nd = {nt: {k: t.clone() for k, t in d.items()} for nt, d in v._ndata.items()}
+        nd = {nt: {k: take(v._ndata[nt][k]) for k in sorted(v._ndata[nt])} for nt in sorted(v._ndata)}
         return HeteroGraph(lazy, v._num_nodes, nd, None, v.idtype, blocks)
     raise ValueError('cannot stage %r' % type(v))
 
@@ -110,18 +140,34 @@ def _entry_tensors(v):
 
 
 class StagedAugmentation:
-    """Persistent buffers holding one augmentation result: `clone()` gives an independent copy with the
-    same structure, `refresh(new)` overwrites the buffers in place with a freshly drawn result."""
+    """Persistent buffers holding one augmentation result, all inside one arena: `clone()` gives an independent copy with
+    the same structure in a twin arena (ONE device copy), `refresh(new)` overwrites the buffers in place with a freshly
+    drawn result (tensor by tensor: the shapes are checked; this runs on the augmentation branch, off the main chain)."""
 
     def __init__(self, aug, base):
         # entries the augmentation left untouched alias the resident inputs and need no staging
         self.keys = [k for k, v in aug.items() if v is not None and v is not base.get(k)]
         self.passthrough = {k: v for k, v in aug.items() if k not in self.keys}
-        self.tree = {k: _clone_entry(aug[k]) for k in self.keys}
+        for k in self.keys:
+            _clone_entry(aug[k], lambda t: t)                      # raises for anything that cannot be staged
+        device = next(t.device for k in self.keys for t in _entry_tensors(aug[k])) if self.keys else 'cpu'
+        self._nbytes = sum(_Arena.span(t) for k in self.keys for t in _entry_tensors(aug[k]))
+        self.arena = _Arena(self._nbytes, device)
+        self.tree = {k: _clone_entry(aug[k], self.arena.take_like) for k in self.keys}
 
     def clone(self):
+        """An independent copy (what `live` is): same structure over a twin arena filled by one device-to-device copy."""
+        twin = _Arena(self._nbytes, self.arena.buf.device)
         out = dict(self.passthrough)
-        out.update({k: _clone_entry(v) for k, v in self.tree.items()})
+        out.update({k: _clone_entry(v, twin.view_like) for k, v in self.tree.items()})
+        import os
+        if os.environ.get('DG_STAGE_ARENA', '1') != '0':
+            twin.buf.copy_(self.arena.buf)
+        else:                                                      # A/B: one copy per tensor, as before the arena
+            for k in self.keys:
+                for d, s_ in zip(_entry_tensors(out[k]), _entry_tensors(self.tree[k])):
+                    d.copy_(s_)
+        self._twins = getattr(self, '_twins', []) + [twin]         # keep the twin alive with its views' owner
         return out
 
     def refresh(self, new):
