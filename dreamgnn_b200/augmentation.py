@@ -33,6 +33,8 @@ def num_keep_edges(num_edges, dropout_rate):
 # (A/B on one box: lrssl 2.46 ms / iteration with randperm vs 2.64 with the select, Gdataset 1.93 vs 1.79 -- inside the
 # run-to-run spread of these latency-chain iterations), so the sampler whose kept sets match the reference's stays
 SELECT_MIN_EDGES = int(os.environ.get('DG_SELECT_MIN_EDGES', str(1 << 20)))
+# ... and at or below this the select is ONE single-CTA launch (select_small_kernel) where the sort is rand + argsort's passes
+SELECT_SMALL_EDGES = int(os.environ.get('DG_SELECT_SMALL_EDGES', str(1 << 14)))
 
 
 def _randperm(n, device):
@@ -42,12 +44,13 @@ def _randperm(n, device):
     given generator state. Inside a CUDA-graph capture (where the generator's offsets already differ from an eager
     run, and torch's small-n randperm, drawn on the CPU, cannot be recorded at all) only the kept SET is needed: an
     `ops.RandomSubset` marker makes `ops.keep_flags` draw a uniformly random num_keep-subset with a sort-free radix
-    select -- the same distribution as randperm[:num_keep] -- for relations of at least SELECT_MIN_EDGES edges.
+    select -- the same distribution as randperm[:num_keep] -- for relations of at least SELECT_MIN_EDGES edges (its
+    passes beat the sort's there) and of at most SELECT_SMALL_EDGES (one single-CTA launch).
     DG_EDGE_SAMPLER=randperm / select forces either."""
     mode = os.environ.get('DG_EDGE_SAMPLER', 'auto')
     on_cuda = th.device(device).type == 'cuda'
     capturing = on_cuda and th.cuda.is_current_stream_capturing()
-    if on_cuda and (mode == 'select' or (mode == 'auto' and capturing and n >= SELECT_MIN_EDGES)):
+    if on_cuda and (mode == 'select' or (mode == 'auto' and capturing and (n >= SELECT_MIN_EDGES or n <= SELECT_SMALL_EDGES))):
         return ops.RandomSubset(n)
     if n < 30000 and capturing:
         return th.argsort(th.rand(n, device=device))

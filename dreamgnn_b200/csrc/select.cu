@@ -12,6 +12,8 @@
 // the edge dropout inside captured CUDA graphs (bench.py, train --cuda_graph), where the generator's offsets differ
 // from an eager run anyway; the eager path keeps th.randperm so that its kept sets are the reference's for a given
 // generator state.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dg {
@@ -83,6 +85,57 @@ __global__ void select_flags_kernel(const long long* __restrict__ rnd, int64_t n
     flags[i] = make_key(rnd[i], i, idx_bits) <= T ? 1 : 0;
 }
 
+// The whole selection for a small relation (n <= kSelectSmall keys: the kNN graphs and the positive-label relations of the
+// real-dataset shapes, a few thousand edges) in ONE single-CTA launch instead of 18: the same eight histogram / pick passes
+// over the same keys (read from L1 / L2 each pass: <= 128 KB), the state in shared memory, then the flags.
+constexpr int kSelectSmall = 16384;
+constexpr int kSelectSmallThreads = 1024;
+__global__ void __launch_bounds__(kSelectSmallThreads)
+select_small_kernel(const long long* __restrict__ rnd, int n, int idx_bits, unsigned long long k, uint8_t* __restrict__ flags) {
+  __shared__ unsigned int h[256];
+  __shared__ unsigned long long wsum[8];
+  __shared__ unsigned long long s_prefix, s_krem;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) { s_prefix = 0; s_krem = k; }
+  for (int pass = 0; pass < 8; ++pass) {
+    if (t < 256) h[t] = 0;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long prefix = s_prefix;
+    for (int i = t; i < n; i += kSelectSmallThreads) {
+      const unsigned long long key = make_key(rnd[i], i, idx_bits);
+      if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&h[(key >> shift) & 255ull], 1u);
+    }
+    __syncthreads();
+    // pick: inclusive scan of the 256 bins by the first 8 warps, exactly as select_pick_kernel
+    unsigned long long mine_cnt = 0, incl = 0;
+    if (t < 256) {
+      mine_cnt = h[t];
+      incl = mine_cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) wsum[warp] = incl;
+    }
+    __syncthreads();
+    const unsigned long long kr = s_krem;
+    if (t < 256) for (int w = 0; w < warp; ++w) incl += wsum[w];
+    __syncthreads();                                          // everyone has read k_rem / wsum before the owner rewrites
+    if (t < 256) {
+      const unsigned long long excl = incl - mine_cnt;
+      if (excl < kr && kr <= incl) {
+        s_prefix = prefix | (static_cast<unsigned long long>(t) << shift);
+        s_krem = kr - excl;
+      }
+    }
+    __syncthreads();
+  }
+  const unsigned long long T = s_prefix;
+  for (int i = t; i < n; i += kSelectSmallThreads) flags[i] = make_key(rnd[i], i, idx_bits) <= T ? 1 : 0;
+}
+
 }  // namespace
 }  // namespace dg
 
@@ -109,6 +162,13 @@ int dg_random_subset_flags(const int64_t* rnd, int64_t n, int64_t k, uint8_t* fl
   }
   int idx_bits = 0;
   while (idx_bits < 40 && (1ll << idx_bits) < n) ++idx_bits;           // bits of n - 1 (n >= 2 here)
+  static const bool small_on = [] { const char* v = getenv("DG_SMALL_PRIMS"); return v == nullptr || atoi(v) != 0; }();   // A/B switch
+  if (n <= kSelectSmall && small_on) {
+    select_small_kernel<<<1, kSelectSmallThreads, 0, s>>>(reinterpret_cast<const long long*>(rnd), static_cast<int>(n), idx_bits,
+                                                          static_cast<unsigned long long>(k), flags);
+    DG_CHECK_LAUNCH("select_small");
+    return DG_OK;
+  }
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = static_cast<int64_t>(kNumSM) * 16;
   if (blocks > cap) blocks = cap;

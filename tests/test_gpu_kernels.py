@@ -582,7 +582,7 @@ def test_spmm_rowsplit_instance(dev, d, weighted, monkeypatch):
 
 
 # ---- sort-free edge-dropout sampler (select.cu) -----------------------------------------------------------
-@pytest.mark.parametrize('n', [1, 2, 5, 257, 100003, 3_000_000])
+@pytest.mark.parametrize('n', [1, 2, 5, 257, 3001, 16384, 16385, 100003, 3_000_000])      # <= 16 384: the one-launch instance
 def test_random_subset_flags_is_the_k_smallest_keys(dev, n):
     """dg_random_subset_flags keeps exactly the num_keep smallest of the keys (rnd << bits(n-1)) | i -- the set a full
     sort of those keys would put first (what randperm[:num_keep] does with torch's keys)."""
