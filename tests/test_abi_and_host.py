@@ -197,3 +197,38 @@ def test_bench_side_files_parse():
     assert 'kernel_digest' in tr and all(isinstance(tr[k], int) for k in tr if k.endswith(('d128', 'd344', 'd768')))
     l2 = json.load(open(os.path.join(REPO, 'profiles', 'l2_peak.json')))
     assert l2['l2_gather_d344']['GBps'] > 1000 and l2['hbm_seq']['GBps'] > 1000
+
+
+def test_arena_gives_twin_layouts_and_one_copy_clone():
+    """graphed._Arena: two arenas filled by the same sequence of requests have identical layouts (256-byte aligned), so a
+    tree of tensors is cloned into its twin by ONE buffer copy; dense entries of a staged augmentation go through it."""
+    from dreamgnn_b200.graphed import StagedAugmentation, _Arena
+    ts = [th.arange(7, dtype=th.int32), th.randn(3, 5), th.zeros(0, 4), th.arange(6, dtype=th.int64).view(2, 3)]
+    a = _Arena(sum(_Arena.span(t) for t in ts), 'cpu')
+    held = [a.take_like(t) for t in ts]
+    assert all(th.equal(h, t) and h.dtype == t.dtype and h.shape == t.shape for h, t in zip(held, ts))
+    assert all(h.data_ptr() % 4 == 0 and (h.data_ptr() - a.buf.data_ptr()) % 256 == 0 for h in held if h.numel())
+    b = _Arena(a.buf.numel(), 'cpu')
+    views = [b.view_like(t) for t in ts]
+    b.buf.copy_(a.buf)
+    assert all(th.equal(v, t) for v, t in zip(views, ts))
+    with pytest.raises(ValueError):
+        b.view_like(th.zeros(1))
+    base = {'drug_feat': th.randn(4, 3), 'disease_feat': th.randn(5, 3), 'enc_graph': None}
+    aug = {'drug_feat': base['drug_feat'] + 1.0, 'disease_feat': base['disease_feat'], 'enc_graph': None}
+    st = StagedAugmentation(aug, base)
+    assert st.keys == ['drug_feat'] and st.passthrough['disease_feat'] is base['disease_feat']
+    live = st.clone()
+    assert th.equal(live['drug_feat'], aug['drug_feat']) and live['drug_feat'].data_ptr() != st.tree['drug_feat'].data_ptr()
+    st.refresh({'drug_feat': aug['drug_feat'] * 2.0})
+    assert th.equal(st.tree['drug_feat'], aug['drug_feat'] * 2.0) and th.equal(live['drug_feat'], aug['drug_feat'])
+    with pytest.raises(ValueError, match='changed shape'):
+        st.refresh({'drug_feat': th.zeros(2, 2)})
+
+
+def test_weighted_loss_sum_on_cpu():
+    xs = [th.tensor(v, requires_grad=True) for v in (0.7, 2.5, -1.25)]
+    total = ops.WeightedLossSum.apply(xs[0], xs[1], xs[2], 0.001)
+    assert abs(float(total) - (0.7 + 0.001 * (2.5 - 1.25))) < 1e-7
+    (total * 2.0).backward()
+    assert [round(float(x.grad), 7) for x in xs] == [2.0, 0.002, 0.002]
