@@ -21,6 +21,11 @@ class AdamTensor(Structure):
     _fields_ = [('param', c_void_p), ('grad', c_void_p), ('exp_avg', c_void_p), ('exp_avg_sq', c_void_p), ('numel', c_int64)]
 
 
+class CopyItem(Structure):
+    """dg_copy_t (include/dreamgnn.h)."""
+    _fields_ = [('dst', c_void_p), ('src', c_void_p), ('bytes', c_int64)]
+
+
 _SIGNATURES = {
     'dg_abi_version': (c_int, []),
     'dg_last_error': (c_char_p, []),
@@ -77,6 +82,7 @@ _SIGNATURES = {
     'dg_adam_workspace_bytes': (c_size_t, [POINTER(AdamTensor), c_int]),
     'dg_adam_clip_step_f32': (c_int, [POINTER(AdamTensor), c_int, _P, _P, c_double, c_double, c_double, c_double, c_double, c_double,
                                       _P, _P, c_size_t, _P]),
+    'dg_multi_copy': (c_int, [POINTER(CopyItem), c_int, _P]),
     'dg_bench_read_rows': (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P, _P]),
 }
 

@@ -142,7 +142,7 @@ def _entry_tensors(v):
 class StagedAugmentation:
     """Persistent buffers holding one augmentation result, all inside one arena: `clone()` gives an independent copy with
     the same structure in a twin arena (ONE device copy), `refresh(new)` overwrites the buffers in place with a freshly
-    drawn result (tensor by tensor: the shapes are checked; this runs on the augmentation branch, off the main chain)."""
+    drawn result (the shapes are checked; one multi-tensor copy launch on the augmentation branch, off the main chain)."""
 
     def __init__(self, aug, base):
         # entries the augmentation left untouched alias the resident inputs and need no staging
@@ -171,11 +171,18 @@ class StagedAugmentation:
         return out
 
     def refresh(self, new):
+        dsts, srcs = [], []
         for k in self.keys:
             dst, src = _entry_tensors(self.tree[k]), _entry_tensors(new[k])
             if len(dst) != len(src) or any(d.shape != s.shape or d.dtype != s.dtype for d, s in zip(dst, src)):
                 raise ValueError('augmentation result %r changed shape between iterations' % k)
-            for d, s in zip(dst, src):
+            dsts += dst
+            srcs += src
+        import os
+        if dsts and dsts[0].is_cuda and os.environ.get('DG_MULTI_COPY', '1') != '0':
+            ops.multi_copy(dsts, [s if s.is_contiguous() else s.contiguous() for s in srcs])      # one launch for all of them
+        else:
+            for d, s in zip(dsts, srcs):
                 d.copy_(s)
 
     def nbytes(self):

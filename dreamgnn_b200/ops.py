@@ -259,6 +259,20 @@ def branches(fns):
 # ------------------------------------------------------------------------------------------------
 # row-streaming helpers (rowops.cu)
 # ------------------------------------------------------------------------------------------------
+def multi_copy(dsts, srcs):
+    """dst.copy_(src) for many same-shaped contiguous CUDA tensor pairs in ONE launch (per 96 pairs)."""
+    lib = L.load()
+    pairs = [(d, s_) for d, s_ in zip(dsts, srcs) if d.numel()]
+    if not pairs:
+        return
+    arr = (L.CopyItem * len(pairs))()
+    for i, (d, s_) in enumerate(pairs):
+        if not (d.is_cuda and s_.is_cuda and d.is_contiguous() and s_.is_contiguous() and d.dtype == s_.dtype and d.shape == s_.shape):
+            raise ValueError('multi_copy: contiguous CUDA tensors of equal dtype and shape expected')
+        arr[i].dst, arr[i].src, arr[i].bytes = d.data_ptr(), s_.data_ptr(), d.numel() * d.element_size()
+    L.check(lib.dg_multi_copy(arr, len(pairs), L.stream()), 'multi_copy')
+
+
 # Zero-initialised int32 tickets lent to kernels that finish in their last CTA (dg_colsum_f32): handed out round-robin from
 # one persistent pool per device, so two calls that may be in flight at the same time (parallel stream branches, or nodes
 # of one captured graph) never share a slot; every kernel leaves its tickets zero again.

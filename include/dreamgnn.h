@@ -335,6 +335,17 @@ DG_API int dg_adam_clip_step_f32(const dg_adam_tensor_t* tensors, int n_tensors,
                           double beta1, double beta2, double eps, double weight_decay, double max_norm, float* norm_out,
                           void* workspace, size_t workspace_bytes, dg_stream_t stream);
 
+/* Many device-to-device copies in one launch (per DG_COPY_MAX_PER_LAUNCH items): `items` is a HOST array of (dst, src, bytes)
+ * triples, copied into the kernel arguments; one CTA per 16 KB chunk of one item, 16-byte accesses when both pointers are
+ * aligned. Ranges must not overlap. Used to refresh the staged augmentation of a captured iteration (~60 tensors). */
+typedef struct {
+  void* dst;
+  const void* src;
+  int64_t bytes;
+} dg_copy_t;
+#define DG_COPY_MAX_PER_LAUNCH 96
+DG_API int dg_multi_copy(const dg_copy_t* items, int n, dg_stream_t stream);
+
 /* ---- measurement support ------------------------------------------------------------------- */
 /* Read-bandwidth microbenchmark with the SpMM's access shape (scripts/l2_peak.py -> profiles/l2_peak.json): every warp
  * of a 148 * ctas_per_sm CTA grid reads `rows_per_warp` rows of `row_floats` fp32 from buf [n_rows, row_floats] with

@@ -337,3 +337,21 @@ def test_small_linear_and_project_autograd(dev, M, K, N, R):
     for got, want in ((x.grad, x64.grad), (w.grad, w64.grad), (b.grad, b64.grad), (wr.grad, wr64.grad)):
         assert H.rel_err(got, want) <= 3e-6
     assert H.rel_err(ops.linear(x.detach(), w.detach()), th.nn.functional.linear(x64, w64)) <= 2e-6      # no bias
+
+
+def test_multi_copy(dev):
+    """dg_multi_copy: many tensors in one launch -- every size class (empty, a few bytes, unaligned views, several 16 KB
+    chunks), more items than one launch carries, mixed dtypes."""
+    from dreamgnn_b200 import ops
+    gen = th.Generator(dev).manual_seed(3)
+    srcs = [th.randn(n, generator=gen, device=dev) for n in (0, 1, 3, 4, 5, 4095, 4096, 4097, 100003)]
+    srcs += [th.randint(0, 1000, (n,), generator=gen, device=dev, dtype=th.int32) for n in (7, 33, 20001)]
+    srcs += [th.randint(0, 255, (n,), generator=gen, device=dev, dtype=th.uint8) for n in (1, 15, 17, 16385)]
+    big = th.randn(5000, generator=gen, device=dev)
+    srcs += [big[1:1 + n] for n in (6, 129, 4001)]                  # 4-byte-aligned but not 16-byte-aligned sources
+    srcs += [th.randn(9, generator=gen, device=dev) for _ in range(120)]            # > 96 items: two launches
+    dsts = [th.full_like(s, 7) for s in srcs]
+    ops.multi_copy(dsts, srcs)
+    assert all(th.equal(d, s) for d, s in zip(dsts, srcs))
+    with pytest.raises(ValueError):
+        ops.multi_copy([th.zeros(4, device=dev)], [th.zeros(5, device=dev)])
