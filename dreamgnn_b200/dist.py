@@ -367,11 +367,16 @@ def all_reduce_gradients(params):
     flat = th.cat([g.reshape(-1) for g in grads])
     with _Timed('all_reduce_gradients', flat.numel() * flat.element_size()):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    off = 0
+    off, parts = 0, []
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        parts.append(flat[off:off + n].view(g.shape))
         off += n
+    if flat.is_cuda and all(g.is_contiguous() for g in grads):
+        ops.multi_copy(grads, parts)                       # one launch instead of one copy per parameter
+    else:
+        for g, p_ in zip(grads, parts):
+            g.copy_(p_)
 
 
 class PartitionedState:
