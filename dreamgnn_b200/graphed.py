@@ -242,7 +242,7 @@ class GraphedIteration:
             else:
                 main = th.cuda.current_stream()
                 self._live = self.staged.clone()                         # live <- staged (the copy every replay runs)
-                self._aug_stream = th.cuda.Stream()
+                self._aug_stream = ops.augmentation_stream(main)
                 self._aug_stream.wait_stream(main)                       # fork: after the copy has read `staged`
                 with th.cuda.stream(self._aug_stream):
                     self.staged.refresh(augment_state(state, aug_methods, aug_params))

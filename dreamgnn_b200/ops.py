@@ -236,13 +236,60 @@ def _each_tensor(x):
             yield from _each_tensor(y)
 
 
+# Side streams of the parallel branches. `th.cuda.Stream()` hands out the 32 streams of torch's per-device pool round-robin,
+# so a process that records several graphs (or just calls `branches` often) sooner or later gets, for a "parallel" branch,
+# the very stream its sibling or the main chain runs on -- the branches then serialise silently (measured: the Cdataset shape
+# 1.24 ms / iteration captured first in a process, 1.45 ms captured after two other shapes). The branches therefore draw
+# from a fixed set of streams with pairwise distinct handles, in the same order in every iteration.
+_SIDE_STREAMS = {}
+_SIDE_NEXT = {}
+_N_SIDE = 12                       # per iteration: routes 1 + node-type halves 4 + common losses 1 < 12; the 13th is the augmentation's
+
+
+def _distinct_streams(device):
+    lst = _SIDE_STREAMS.get(device)
+    if lst is None:
+        lst = _SIDE_STREAMS[device] = []
+        for _ in range(64):
+            s = th.cuda.Stream(device=device)
+            if all(s.cuda_stream != t.cuda_stream for t in lst):
+                lst.append(s)
+            if len(lst) == _N_SIDE + 1:
+                break
+    return lst
+
+
+def side_stream(main):
+    """The next side stream of this iteration's branches: never the stream `main` itself."""
+    lst = _distinct_streams(main.device)[:_N_SIDE]
+    i = _SIDE_NEXT.get(main.device, 0)
+    for _ in range(len(lst)):
+        s = lst[i % len(lst)]
+        i += 1
+        if s.cuda_stream != main.cuda_stream:
+            break
+    _SIDE_NEXT[main.device] = i
+    return s
+
+
+def augmentation_stream(main):
+    """The stream of the pipelined augmentation branch (held for a whole iteration: its own slot)."""
+    s = _distinct_streams(main.device)[-1]
+    return s if s.cuda_stream != main.cuda_stream else th.cuda.Stream(device=main.device)
+
+
+def reset_side_streams(device):
+    """Start of an iteration: its branches take the side streams in the same order as every other iteration's."""
+    _SIDE_NEXT[th.device(device)] = 0
+
+
 def branches(fns):
     """Results of the independent closures `fns`, in order. With PARALLEL_BRANCHES the first runs on the current
     stream and each other one on its own side stream forked from / joined to it."""
     if not PARALLEL_BRANCHES or len(fns) < 2 or not th.cuda.is_available():
         return [f() for f in fns]
     main = th.cuda.current_stream()
-    sides = [th.cuda.Stream(device=main.device) for _ in fns[1:]]
+    sides = [side_stream(main) for _ in fns[1:]]
     out = [None] * len(fns)
     for i, st in enumerate(sides, start=1):
         st.wait_stream(main)
@@ -531,10 +578,12 @@ _SEED_POOLS = {}
 
 
 def begin_seed_pool(device):
-    """Draw this iteration's dropout seeds (one launch). Call on the stream the iteration's branches fork from."""
+    """Start of a training iteration: draw its dropout seeds (one launch) and rewind the side streams of its parallel
+    branches. Call on the stream the iteration's branches fork from."""
     device = th.device(device)
     if device.type == 'cuda':
         _SEED_POOLS[device] = _SeedPool(device)
+        reset_side_streams(device)
 
 
 def drop_seed_pool(device=None):

@@ -130,7 +130,7 @@ def train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_param
         # the common losses need only the route outputs: a side branch forked where those were complete, beside the
         # attention + decoder + BCE (and, in the backward, beside the decoder's backward); joined for the total
         main = th.cuda.current_stream()
-        side = th.cuda.Stream(device=main.device)
+        side = ops.side_stream(main)
         side.wait_event(ready)
         with th.cuda.stream(side):
             c_drug, c_dis = common_loss_fn(drug_out, drug_sim_out), common_loss_fn(dis_out, dis_sim_out)
