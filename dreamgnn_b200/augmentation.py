@@ -105,8 +105,8 @@ class GraphAugmentation:
             pos = th.empty(max(getattr(base, 'parent_nnz', 0), base.nnz, 1), dtype=th.int32, device=base.device)
             pos[base.eid.long()] = th.arange(base.nnz, dtype=th.int32, device=base.device)
             t = base.transpose()
-            nb = ops.CSR(base.indptr, base.indices, pos[base.eid.long()], base.vals, base.n_rows, base.n_cols)
-            nt = ops.CSR(t.indptr, t.indices, pos[t.eid.long()], t.vals, t.n_rows, t.n_cols)
+            nb = ops.inherit_layout(ops.CSR(base.indptr, base.indices, pos[base.eid.long()], base.vals, base.n_rows, base.n_cols), base)
+            nt = ops.inherit_layout(ops.CSR(t.indptr, t.indices, pos[t.eid.long()], t.vals, t.n_rows, t.n_cols), t)
             nb._t, nt._t = nt, nb
             nb.slot_order = nb.eid_is_slot = True
             sparse_graph._dg_csr = base = nb
@@ -195,11 +195,11 @@ class GraphAugmentation:
         # a base graph (eid = COO position); a dropped graph's COO is always in slot order (_sparse_from_csr)
         def regather(c):
             return noisy.contiguous() if (c is base and base.slot_order) else noisy[_coo_position(c, base).long()].contiguous()
-        csr = ops.CSR(base.indptr, base.indices, base.eid, regather(base), base.n_rows, base.n_cols)
+        csr = ops.inherit_layout(ops.CSR(base.indptr, base.indices, base.eid, regather(base), base.n_rows, base.n_cols), base)
         csr.slot_order, csr.eid_is_slot, csr.parent_nnz = base.slot_order, base.eid_is_slot, base.parent_nnz
         if base._t is not None:
             t = base._t
-            ct = ops.CSR(t.indptr, t.indices, t.eid, regather(t), t.n_rows, t.n_cols)
+            ct = ops.inherit_layout(ops.CSR(t.indptr, t.indices, t.eid, regather(t), t.n_rows, t.n_cols), t)
             ct.slot_order, ct.eid_is_slot, ct.parent_nnz = t.slot_order, t.eid_is_slot, t.parent_nnz
             csr._t, ct._t = ct, csr
         out._dg_csr = csr

@@ -83,6 +83,7 @@ def _clone_csr(c, take):
     def one(x):
         n = ops.CSR(take(x.indptr), take(x.indices), take(x.eid), None if x.vals is None else take(x.vals), x.n_rows, x.n_cols)
         n.slot_order, n.eid_is_slot, n.parent_nnz = x.slot_order, x.eid_is_slot, x.parent_nnz
+        ops.inherit_layout(n, x)
         return n
     n = one(c)
     if c._t is not None:

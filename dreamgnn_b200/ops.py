@@ -27,6 +27,17 @@ SPMM_ROWSPLIT_MAX_ROWS, SPMM_ROWSPLIT_MIN_AVG_LEN = 2368, 128
 # (d=128, 94 % hit rate) lose ~20 % to the extra instructions -- hence the switch on operand size and row width.
 SPMM_PREFETCH_MIN_BYTES = int(os.environ.get('DG_SPMM_PREFETCH_MIN_MB', '120')) << 20          # any row width
 SPMM_PREFETCH_MIN_BYTES_WIDE = int(os.environ.get('DG_SPMM_PREFETCH_MIN_MB_WIDE', '48')) << 20   # rows of >= 1 KiB
+# Skewed graphs (a few rows of 10^4...10^5 edges among rows of 10^1...10^2: Zipf popularity, SURVEY.md 8d "secondary stress
+# set"): warp-per-row leaves the launch waiting on the one warp that walks the longest row. Measured on the Zipf(1.0)
+# variant of syn20m (13.9 M pairs, two 50 000-edge rows, median 34; d=344): 9.17 ms in one launch against cuSPARSE's 2.42 ms.
+# A CSR whose longest row exceeds SPMM_SPLIT_MIN_DEG at build time is therefore aggregated in two launches of the same
+# kernel: the rows cut into chunks of <= SPMM_SPLIT_T edges (a second indptr over the SAME indices / values), then the
+# chunk partials summed per row in chunk order with the epilogue (ci, bias, ReLU) applied there -- deterministic, no
+# atomics. Same graph: 1.49 ms at T=128 (1.55 / 1.70 / 1.92 / 2.23 ms at 256 / 512 / 1024 / 2048), i.e. 1.6x cuSPARSE
+# (profiles/r02c_library_compare.md). Uniform shapes (every BASELINE config: longest row <= ~1 000) never take this path.
+SPMM_SPLIT = os.environ.get('DG_SPMM_SPLIT', '1') != '0'
+SPMM_SPLIT_T = int(os.environ.get('DG_SPMM_SPLIT_T', '128'))
+SPMM_SPLIT_MIN_DEG = int(os.environ.get('DG_SPMM_SPLIT_MIN_DEG', '4096'))
 
 
 def _i32(t, name):
@@ -76,7 +87,8 @@ class CSR:
     variants of one graph stay consistent.
     """
 
-    __slots__ = ('indptr', 'indices', 'eid', 'vals', 'n_rows', 'n_cols', '_t', 'slot_order', 'eid_is_slot', 'parent_nnz')
+    __slots__ = ('indptr', 'indices', 'eid', 'vals', 'n_rows', 'n_cols', '_t', 'slot_order', 'eid_is_slot', 'parent_nnz',
+                 'split_T', '_plan')
 
     def __init__(self, indptr, indices, eid, vals, n_rows, n_cols):
         self.indptr, self.indices, self.eid, self.vals = indptr, indices, eid, vals
@@ -85,6 +97,8 @@ class CSR:
         self.slot_order = False     # True when the owning COO tensor lists its entries in slot order
         self.eid_is_slot = False    # True when eid[s] == s (ids already name this tensor's own entries)
         self.parent_nnz = 0         # edge-dropped CSR: entry count of the graph its eids refer to (sizes id lookups)
+        self.split_T = 0            # > 0: rows are aggregated in chunks of this many edges (skewed graphs; see split_plan)
+        self._plan = None           # cached split_plan of this CSR
 
     @property
     def nnz(self):
@@ -113,7 +127,13 @@ class CSR:
             v = vals.contiguous()[eid.long()]
         if edge_ids is not None:
             eid = _i32(edge_ids, 'edge_ids')[eid.long()]
-        return CSR(indptr, indices, eid, v, n_rows, n_cols)
+        csr = CSR(indptr, indices, eid, v, n_rows, n_cols)
+        if SPMM_SPLIT and n > SPMM_SPLIT_MIN_DEG and n_rows > 0:
+            # one host read per graph BUILD (from_coo already reads the index range back); derived structures -- dropout
+            # compactions, staged clones, re-valued copies -- inherit the decision and never synchronise
+            if int((indptr[1:] - indptr[:-1]).max()) > SPMM_SPLIT_MIN_DEG:
+                csr.split_T = SPMM_SPLIT_T
+        return csr
 
     def rows(self):
         """COO row id of every slot."""
@@ -139,6 +159,36 @@ class CSR:
         out = th.empty(self.n_rows, dtype=th.float32, device=self.device)
         L.check(lib.dg_degree_norm(L.ptr(self.indptr), self.n_rows, L.ptr(out), L.stream()), 'degree_norm')
         return out
+
+
+def inherit_layout(new, base):
+    """`new` is a structure derived from `base` with the same row population (compaction, clone, re-valued copy):
+    it keeps base's chunked-aggregation decision. Returns `new`."""
+    new.split_T = base.split_T
+    return new
+
+
+def split_plan(indptr, n_rows, nnz, T):
+    """Chunked view of a CSR for rows far longer than the rest (pure index arithmetic on the device, static shapes, no
+    host read: capturable, and runs on CPU tensors for the tests).
+
+    Row r of `deg` edges becomes max(1, ceil(deg / T)) consecutive virtual rows of <= T edges each. Returns
+      v_indptr    int32 [n_v + 1]   indptr of the virtual rows over the SAME indices / values arrays,
+      comb_indptr int32 [n_rows + 1] row r's virtual rows are comb_indptr[r] .. comb_indptr[r + 1] - 1, in edge order,
+      n_v         = n_rows + nnz // T, a static upper bound on the number of virtual rows (the unused tail is empty rows).
+    """
+    n_v = int(n_rows) + int(nnz) // int(T)
+    ip = indptr.long()
+    deg = ip[1:] - ip[:-1]
+    nch = ((deg + (T - 1)) // T).clamp_(min=1)
+    vend = th.cumsum(nch, 0)                                   # inclusive: first virtual row AFTER row r
+    vbeg = vend - nch
+    v = th.arange(n_v + 1, device=indptr.device)
+    r = th.searchsorted(vend, v, right=True).clamp_(max=int(n_rows) - 1)
+    start = th.minimum(ip[:-1][r] + (v - vbeg[r]) * T, ip[1:][r])      # past the last real chunk: == nnz (empty rows)
+    comb = th.zeros(int(n_rows) + 1, dtype=I32, device=indptr.device)
+    comb[1:] = vend
+    return start.to(I32), comb, n_v
 
 
 class RandomSubset:
@@ -187,7 +237,7 @@ def csr_compact(csr, flags, n_keep):
     L.check(lib.dg_csr_compact(L.ptr(csr.indptr), L.ptr(csr.indices), L.ptr(csr.eid), L.ptr(csr.vals), csr.n_rows,
                                L.ptr(flags, th.uint8, 'flags'), L.ptr(indptr), L.ptr(indices), L.ptr(eid),
                                L.ptr(vals), L.ptr(ws), ws.numel(), L.stream()), 'csr_compact')
-    return CSR(indptr, indices, eid, vals, csr.n_rows, csr.n_cols)
+    return inherit_layout(CSR(indptr, indices, eid, vals, csr.n_rows, csr.n_cols), csr)
 
 
 def csr_dropout(csr, flags, n_keep):
@@ -745,6 +795,16 @@ def _spmm_raw(csr, x, src_scale=None, dst_scale=None, bias=None, flags=0, out=No
     for nm, t, n in (('src_scale', src_scale, csr.n_cols), ('dst_scale', dst_scale, csr.n_rows), ('bias', bias, d)):
         if t is not None and (t.numel() != n or t.dtype != th.float32):
             raise ValueError('spmm: %s must be fp32 with %d elements' % (nm, n))
+    if csr.split_T and csr.nnz and not (flags & SPMM_ACCUMULATE):
+        # skewed graph: chunk partials (src_scale applied), then the per-row sum of the chunks with the epilogue
+        if csr._plan is None:
+            v_indptr, comb_indptr, n_v = split_plan(csr.indptr, csr.n_rows, csr.nnz, csr.split_T)
+            chunks = CSR(v_indptr, csr.indices, csr.eid, csr.vals, n_v, csr.n_cols)
+            comb = CSR(comb_indptr, th.arange(n_v, dtype=I32, device=x.device), None, None, csr.n_rows, n_v)
+            csr._plan = (chunks, comb)
+        chunks, comb = csr._plan
+        part = _spmm_raw(chunks, x, src_scale, None, None, 0, tag=tag)
+        return _spmm_raw(comb, part, None, dst_scale, bias, flags & SPMM_RELU, out=out, tag=tag + '.combine')
     if 0 < csr.n_rows <= SPMM_ROWSPLIT_MAX_ROWS and csr.nnz >= SPMM_ROWSPLIT_MIN_AVG_LEN * csr.n_rows:
         flags |= SPMM_ROWSPLIT
     operand = csr.n_cols * d * x.element_size()

@@ -3,7 +3,7 @@ There is no network for the real `.mat` files, so every measured configuration i
 the named shape with random-initialised weights; bench.py says so in its `data` field.
 
   * `sparse_workload`  -- the 20M / 400M-association shapes: distinct uniform cells of the drug x
-    disease grid, Bernoulli(pos_rate) labels, row-L2-normalised N(0,1) features (1024 / 768 wide, so
+    disease grid (or, with spec['pair_dist'] = 'zipf', Zipf(1.0) drug popularity: the secondary stress set), Bernoulli(pos_rate) labels, row-L2-normalised N(0,1) features (1024 / 768 wide, so
     the unequal-dims branch of GCMCLayer is exercised), k=15 kNN graphs from cosine similarity.
     FGCN's input is the feature matrix (the reference feeds the dense N x N similarity, impossible
     at 100k nodes) -- the one stated departure of these shapes.
@@ -46,11 +46,28 @@ def _features(n, f, gen, device):
     return F.normalize(th.randn(n, f, generator=gen, device=device), p=2, dim=1)      # data_loader.py:221-222
 
 
+def zipf_cells(n_d, n_s, n_draws, gen, device, s=1.0):
+    """The secondary stress set of SURVEY.md 8d config 4: `n_draws` (drug, disease) cells with Zipf(s) drug popularity
+    (drug of popularity rank r drawn with probability proportional to 1 / r^s; which drug holds which rank is a seeded
+    permutation) and uniform diseases; duplicates removed, so fewer than `n_draws` distinct cells come back -- the most
+    popular drugs saturate at every disease. Row lengths of the drug-side CSR then span 1 ... n_s."""
+    w = th.arange(1, n_d + 1, device=device, dtype=th.float64).pow_(-float(s))
+    cdf = th.cumsum(w, 0)
+    cdf /= cdf[-1].clone()
+    rank = th.searchsorted(cdf, th.rand(n_draws, generator=gen, device=device, dtype=th.float64)).clamp_(max=n_d - 1)
+    drug = th.randperm(n_d, generator=gen, device=device)[rank]
+    dis = th.randint(0, n_s, (n_draws,), generator=gen, device=device)
+    return th.unique(drug * n_s + dis)
+
+
 def sparse_workload(spec, device, seed=1234, pos_rate=0.01, sim_dim=64):
     device = th.device(device)
     gen = th.Generator(device).manual_seed(seed)
     n_d, n_s = spec['n_drug'], spec['n_dis']
-    cells = th.unique(th.randint(0, n_d * n_s, (spec['n_pairs'],), generator=gen, device=device))
+    if spec.get('pair_dist', 'uniform') == 'zipf':
+        cells = zipf_cells(n_d, n_s, spec['n_pairs'], gen, device)
+    else:
+        cells = th.unique(th.randint(0, n_d * n_s, (spec['n_pairs'],), generator=gen, device=device))
     labels = (th.rand(cells.numel(), generator=gen, device=device) < pos_rate).float()
     order = th.argsort(labels, descending=True, stable=True)            # positives first (data_loader.py:170-183)
     cells, labels = cells[order], labels[order].contiguous()

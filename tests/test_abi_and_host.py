@@ -232,3 +232,87 @@ def test_weighted_loss_sum_on_cpu():
     assert abs(float(total) - (0.7 + 0.001 * (2.5 - 1.25))) < 1e-7
     (total * 2.0).backward()
     assert [round(float(x.grad), 7) for x in xs] == [2.0, 0.002, 0.002]
+
+
+@pytest.mark.parametrize('T', [1, 4, 7, 64])
+def test_split_plan_tiles_every_row_in_order(T):
+    """ops.split_plan (chunked aggregation of skewed CSRs): the virtual rows tile each real row exactly, in edge order,
+    in chunks of <= T; the unused tail of the static bound is empty; chunk sums then row sums equal the direct sums."""
+    rng = np.random.default_rng(T)
+    deg = np.concatenate([[0, 0, 1, T, T + 1, 5 * T, 37 * T + 3], rng.integers(0, 3 * T + 2, 40), [0]])
+    rng.shuffle(deg)
+    indptr = th.tensor(np.concatenate([[0], np.cumsum(deg)]), dtype=th.int32)
+    n_rows, nnz = len(deg), int(deg.sum())
+    v_indptr, comb, n_v = ops.split_plan(indptr, n_rows, nnz, T)
+    assert n_v == n_rows + nnz // T and v_indptr.dtype == comb.dtype == th.int32
+    assert v_indptr.numel() == n_v + 1 and comb.numel() == n_rows + 1
+    v, c = v_indptr.numpy().astype(np.int64), comb.numpy().astype(np.int64)
+    assert v[0] == 0 and v[-1] == nnz and (np.diff(v) >= 0).all() and (np.diff(v) <= T).all()
+    assert c[0] == 0 and c[-1] <= n_v and (np.diff(c) == np.maximum(1, -(-deg // T))).all()
+    for r in range(n_rows):
+        assert v[c[r]] == indptr[r] and v[c[r + 1]] == indptr[r + 1]           # row r = its chunks, contiguous
+        assert (np.diff(v[c[r]:c[r + 1] + 1])[:-1] == T).all()                   # all but the last chunk are full
+    assert (v[c[-1]:] == nnz).all()                                              # tail: empty rows
+    # two-pass sums == direct sums (integers: exact)
+    w = th.tensor(rng.integers(-5, 6, nnz), dtype=th.float64)
+    seg = lambda ptr, x: th.stack([x[int(ptr[i]):int(ptr[i + 1])].sum() for i in range(len(ptr) - 1)]) if len(ptr) > 1 else x[:0]
+    assert th.equal(seg(c, seg(v, w)), seg(indptr.numpy(), w))
+
+
+def test_split_decision_is_inherited_by_derived_structures():
+    base = ops.CSR(th.tensor([0, 2]), th.tensor([0, 1]), th.tensor([0, 1]), None, 1, 2)
+    assert base.split_T == 0 and base._plan is None
+    base.split_T = 512
+    assert ops.inherit_layout(ops.CSR(base.indptr, base.indices, base.eid, None, 1, 2), base).split_T == 512
+    from dreamgnn_b200 import graphed
+    assert graphed._clone_csr(base, lambda t: t.clone()).split_T == 512
+
+
+def test_chunked_spmm_composition_with_a_stand_in_kernel(monkeypatch):
+    """Host logic of the skewed-graph SpMM path (ops._spmm_raw with csr.split_T): with the C entry point replaced by a
+    torch stand-in of its contract (out = relu?(ds * (A (ss * x)) + bias)), the two launches -- chunk partials, then per-row
+    sums with the epilogue -- compose to exactly what one launch gives. (The kernel itself is covered by the GPU tests.)"""
+    calls = []
+
+    class FakeLib:
+        @staticmethod
+        def dg_spmm_csr_f32(indptr, indices, vals, ss, ds, bias, x, x_stride, out, out_stride, n_rows, d, flags, stream):
+            calls.append((int(n_rows), int(flags)))
+            assert indptr.numel() == n_rows + 1 and out.shape == (n_rows, d)
+            rows = th.repeat_interleave(th.arange(n_rows), (indptr[1:] - indptr[:-1]).long())
+            nnz = int(indptr[-1])
+            g = x.double()[indices[:nnz].long()] * (1.0 if ss is None else ss.double()[indices[:nnz].long()][:, None])
+            if vals is not None:
+                g = g * vals.double()[:nnz, None]
+            acc = th.zeros(n_rows, d, dtype=th.float64).index_add_(0, rows, g)
+            if ds is not None:
+                acc = acc * ds.double()[:, None]
+            if bias is not None:
+                acc = acc + bias.double()
+            out.copy_(acc.relu() if flags & ops.SPMM_RELU else acc)
+            return 0
+
+    class FakeL:
+        load = staticmethod(lambda: FakeLib)
+        ptr = staticmethod(lambda t, *a: t)
+        check = staticmethod(lambda rc, what: None)
+        stream = staticmethod(lambda: 0)
+    monkeypatch.setattr(ops, 'L', FakeL)
+    rng = np.random.default_rng(0)
+    deg = np.concatenate([[0, 300, 1, 0, 77], rng.integers(0, 9, 30)])
+    indptr = th.tensor(np.concatenate([[0], np.cumsum(deg)]), dtype=th.int32)
+    nnz, n_rows, n_cols, d = int(deg.sum()), len(deg), 50, 8
+    g = th.Generator().manual_seed(0)
+    indices = th.randint(0, n_cols, (nnz,), generator=g, dtype=th.int32)
+    vals = th.randint(1, 4, (nnz,), generator=g).float()
+    x = th.randint(-3, 4, (n_cols, d), generator=g).float()                 # small integers: every sum is exact
+    ss, ds = th.randint(1, 3, (n_cols,), generator=g).float(), th.randint(1, 3, (n_rows,), generator=g).float()
+    bias = th.randint(-2, 3, (d,), generator=g).float()
+    csr = ops.CSR(indptr, indices, th.arange(nnz, dtype=th.int32), vals, n_rows, n_cols)
+    one = ops._spmm_raw(csr, x, ss, ds, bias, ops.SPMM_RELU)
+    assert len(calls) == 1
+    csr.split_T = 16
+    two = ops._spmm_raw(csr, x, ss, ds, bias, ops.SPMM_RELU)
+    assert [c[0] for c in calls[1:]] == [n_rows + nnz // 16, n_rows] and calls[1][1] & ops.SPMM_RELU == 0
+    assert th.equal(one, two) and csr._plan is not None
+    assert th.equal(ops._spmm_raw(csr, x, ss, ds, bias, ops.SPMM_RELU), one) and len(calls) == 5       # cached plan

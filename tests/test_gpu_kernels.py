@@ -184,6 +184,56 @@ def test_spmm_rejects_bad_layout(dev):
         o.spmm(csr, th.randn(1, 5, device=dev))
 
 
+@pytest.mark.parametrize('d', [128, 344])
+@pytest.mark.parametrize('weighted,scaled,epi', [(False, True, False), (True, True, True)])
+def test_spmm_chunked_aggregation_of_skewed_rows(dev, d, weighted, scaled, epi):
+    """A graph with a 5 000-edge row and a 4 500-edge column (Zipf stress set): from_coo flags both orientations
+    for chunked aggregation (ops.split_plan: chunk partials, then per-row sums with the epilogue); forward and backward
+    equal the dense float64 restatement, equal the one-launch path up to summation order, and are deterministic."""
+    rng = np.random.default_rng(d + weighted)
+    n_rows, n_cols = 6000, 5000
+    row = np.concatenate([np.full(n_cols, 7), rng.choice(n_rows, 4500, replace=False), rng.integers(0, n_rows, 20000)])
+    col = np.concatenate([np.arange(n_cols), np.full(4500, 11), rng.integers(0, n_cols, 20000)])
+    e = len(row)
+    val = rng.random(e).astype(np.float32) if weighted else None
+    g = th.Generator().manual_seed(d)
+    x = th.randn(n_cols, d, generator=g)
+    ss, ds = (th.rand(n_cols, generator=g), th.rand(n_rows, generator=g)) if scaled else (None, None)
+    bias = th.randn(d, generator=g) if epi else None
+    o = ops()
+    mk = lambda: o.CSR.from_coo(th.tensor(row, device=dev), th.tensor(col, device=dev), n_rows, n_cols,
+                                th.tensor(val, device=dev) if weighted else None)
+    csr = mk()
+    assert csr.split_T == o.SPMM_SPLIT_T and csr.transpose().split_T == o.SPMM_SPLIT_T
+    to = lambda t: None if t is None else t.to(dev)
+    xg = x.to(dev).requires_grad_(True)
+    bg = bias.to(dev).requires_grad_(True) if epi else None
+    out = o.spmm(csr, xg, to(ss), to(ds), bg, relu=epi)
+    assert csr._plan is not None and csr._plan[0].n_rows == n_rows + e // o.SPMM_SPLIT_T
+    want = _dense_spmm(row, col, val, n_rows, x, ss, ds, bias, epi)
+    assert H.rel_err(out.detach().cpu(), want) <= FP32_TOL
+    gout = th.randn(n_rows, d, generator=g)
+    out.backward(gout.to(dev))
+    xr = x.clone().double().requires_grad_(True)
+    br = bias.clone().double().requires_grad_(True) if epi else None
+    _dense_spmm(row, col, val, n_rows, xr, ss, ds, br, epi).backward(gout.double())
+    assert H.rel_err(xg.grad.cpu(), xr.grad) <= FP32_TOL
+    if epi:
+        assert H.rel_err(bg.grad.cpu(), br.grad) <= FP32_TOL
+    assert th.equal(o.spmm(csr, xg.detach(), to(ss), to(ds), None if bg is None else bg.detach(), relu=epi), out.detach())
+    # the one-launch path on the same graph: same sums in another order
+    plain = mk()
+    plain.split_T = 0
+    plain.transpose().split_T = 0
+    one = o.spmm(plain, xg.detach(), to(ss), to(ds), None if bg is None else bg.detach(), relu=epi)
+    assert plain._plan is None and H.rel_err(out.detach().cpu(), one.cpu()) <= 2e-6
+    # a dropout compaction keeps the decision in both orientations
+    flags = th.ones(e, dtype=th.uint8, device=dev)
+    dropped = o.csr_dropout(csr, flags, e)
+    assert dropped.split_T == o.SPMM_SPLIT_T and dropped.transpose().split_T == o.SPMM_SPLIT_T
+    assert th.equal(o.spmm(dropped, xg.detach(), to(ss), to(ds), None if bg is None else bg.detach(), relu=epi), out.detach())
+
+
 # ---- decoder ---------------------------------------------------------------------------------------
 def _decoder_params(gen, n_in):
     P = {'decoder.lin1.weight': th.randn(128, 2 * n_in, generator=gen) * 0.2,
