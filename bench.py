@@ -652,15 +652,25 @@ def run_b200(args):
     del res
 
     if world == 1 and not args.no_cpu_baseline:
-        base = cpu_reference(args.workload, args.scale, steps=1, warmup=1, cpu_scale=args.cpu_scale)
+        try:
+            base = cpu_reference(args.workload, args.scale, steps=1, warmup=1, cpu_scale=args.cpu_scale)
+        except Exception as e:                                   # noqa: BLE001 -- never lose the main line
+            import traceback
+            traceback.print_exc()
+            base = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:300] if str(e) else '')}
         # the GPU arm on EXACTLY the sample the CPU arm ran: the same-workload ratio
         if 'sample_scale' in base:
-            g = measure(ctx, args.workload, base['sample_scale'], steps=20, warmup=3, cuda_graph=args.cuda_graph, e2e=True, seed=1234)
-            base['same_shape'] = {'workload': '%s at scale %.5g: %d drugs x %d diseases, %d scored pairs'
-                                              % (args.workload, base['sample_scale'], g['spec']['n_drug'], g['spec']['n_dis'], g['n_pairs']),
-                                  'gpu_ms_per_step': round(g['ms_per_step'], 3), 'gpu_e2e_ms_per_step': round(g['e2e_ms_per_step'], 3),
-                                  'cpu_ms_per_step': base['ms_per_step'], 'ratio': round(base['ms_per_step'] / g['ms_per_step'], 1),
-                                  'e2e_ratio': round(base['ms_per_step'] / g['e2e_ms_per_step'], 1), 'same_config': True}
+            try:
+                g = measure(ctx, args.workload, base['sample_scale'], steps=20, warmup=3, cuda_graph=args.cuda_graph, e2e=True, seed=1234)
+                base['same_shape'] = {'workload': '%s at scale %.5g: %d drugs x %d diseases, %d scored pairs'
+                                                  % (args.workload, base['sample_scale'], g['spec']['n_drug'], g['spec']['n_dis'], g['n_pairs']),
+                                      'gpu_ms_per_step': round(g['ms_per_step'], 3), 'gpu_e2e_ms_per_step': round(g['e2e_ms_per_step'], 3),
+                                      'cpu_ms_per_step': base['ms_per_step'], 'ratio': round(base['ms_per_step'] / g['ms_per_step'], 1),
+                                      'e2e_ratio': round(base['ms_per_step'] / g['e2e_ms_per_step'], 1), 'same_config': True}
+            except Exception as e:                               # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                base['same_shape'] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:300] if str(e) else '')}
         out['cpu_baseline'] = base
         if (args.workload == 'syn20m' and args.scale == 1.0 and not args.no_extra) or args.extra:
             out['extra_workloads'] = extra_workloads(ctx, args)

@@ -173,7 +173,6 @@ def train(args, dataset, cv):
     """Mirror of train.py:154-395: one fold. `dataset` must expose the reference loader's attributes
     (`drug_feature`, `disease_feature`, `*_feature_shape`, `drug_sim_features`, `disease_sim_features`,
     `cv_data_dict`, `data_cv`, `cv_specific_graphs`) with graphs built by dreamgnn_b200.graph_build."""
-    from .evaluation import evaluate
     args.src_in_units = dataset.drug_feature_shape[1]
     args.dst_in_units = dataset.disease_feature_shape[1]
     args.fdim_drug = dataset.drug_feature_shape[0]
@@ -190,6 +189,16 @@ def train(args, dataset, cv):
     entry_stream = th.cuda.current_stream() if use_graph else None
     if use_graph and entry_stream == th.cuda.default_stream():
         th.cuda.set_stream(th.cuda.Stream())       # graph capture cannot involve the legacy default stream
+    try:
+        return _train_fold(args, dataset, cv, dev, state, model, rel_loss_fn, use_graph, train_data_dict, test_data_dict)
+    finally:
+        if entry_stream is not None:
+            th.cuda.set_stream(entry_stream)       # leave the caller's stream current again, also when a fold fails
+
+
+def _train_fold(args, dataset, cv, dev, state, model, rel_loss_fn, use_graph, train_data_dict, test_data_dict):
+    """The loop of train.py:211-395 for one fold (split from `train` so that the stream it switched is always restored)."""
+    from .evaluation import evaluate
     # graph mode: the learning rate lives in a device tensor, which the captured Adam step reads on every replay and
     # ReduceLROnPlateau updates in place -- a scheduler step takes effect without re-capturing
     lr = th.tensor(float(args.train_lr), device=dev) if use_graph else args.train_lr
@@ -211,28 +220,30 @@ def train(args, dataset, cv):
         # the eager warm-up iterations before the capture are real optimiser steps: they count as training iterations,
         # so a fold makes exactly train_max_iter - 1 updates as in the reference loop (train.py:250)
         first_it = 1 + graphed.eager_iterations
-    for it in range(first_it, args.train_max_iter):
-        if graphed is not None:
-            total = graphed()
-        else:
-            total = train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_params, args.beta,
-                                    args.train_grad_clip)
-        if it % args.train_valid_interval == 0:
-            ev = lambda d: evaluate(args, model, d, state.drug_graph, state.drug_feat, state.drug_sim_feat,
-                                    state.dis_graph, state.dis_feat, state.dis_sim_feat, state.drug_feature_graph,
-                                    state.disease_feature_graph)
-            tr_auroc, tr_aupr = ev(train_data_dict)
-            te_auroc, te_aupr = ev(test_data_dict)
-            scheduler.step(te_aupr)
-            log.write('%d,%.4f,%.4f,%.4f,%.4f,%.4f\n' % (it, total.item(), tr_auroc, tr_aupr, te_auroc, te_aupr))
-            log.flush()
-            print('Iter=%5d, Loss=%.4f, Train: AUROC=%.4f, AUPR=%.4f, Test: AUROC=%.4f, AUPR=%.4f'
-                  % (it, total.item(), tr_auroc, tr_aupr, te_auroc, te_aupr))
-            if te_aupr > best['aupr']:
-                best.update(aupr=te_aupr, auroc=te_auroc, it=it, train_aupr=tr_aupr, train_auroc=tr_auroc)
-                if getattr(args, 'save_model', False):
-                    th.save(model.state_dict(), os.path.join(args.save_dir, 'best_model_fold%s.pth' % args.save_id))
-    log.close()
+    try:
+        for it in range(first_it, args.train_max_iter):
+            if graphed is not None:
+                total = graphed()
+            else:
+                total = train_iteration(model, optimizer, state, rel_loss_fn, aug_methods, aug_params, args.beta,
+                                        args.train_grad_clip)
+            if it % args.train_valid_interval == 0:
+                ev = lambda d: evaluate(args, model, d, state.drug_graph, state.drug_feat, state.drug_sim_feat,
+                                        state.dis_graph, state.dis_feat, state.dis_sim_feat, state.drug_feature_graph,
+                                        state.disease_feature_graph)
+                tr_auroc, tr_aupr = ev(train_data_dict)
+                te_auroc, te_aupr = ev(test_data_dict)
+                scheduler.step(te_aupr)
+                log.write('%d,%.4f,%.4f,%.4f,%.4f,%.4f\n' % (it, total.item(), tr_auroc, tr_aupr, te_auroc, te_aupr))
+                log.flush()
+                print('Iter=%5d, Loss=%.4f, Train: AUROC=%.4f, AUPR=%.4f, Test: AUROC=%.4f, AUPR=%.4f'
+                      % (it, total.item(), tr_auroc, tr_aupr, te_auroc, te_aupr))
+                if te_aupr > best['aupr']:
+                    best.update(aupr=te_aupr, auroc=te_auroc, it=it, train_aupr=tr_aupr, train_auroc=tr_auroc)
+                    if getattr(args, 'save_model', False):
+                        th.save(model.state_dict(), os.path.join(args.save_dir, 'best_model_fold%s.pth' % args.save_id))
+    finally:
+        log.close()
     print('Running time:', time.strftime('%H:%M:%S', time.gmtime(round(time.perf_counter() - start))))
     with open(os.path.join(args.save_dir, 'best_metric%s.csv' % args.save_id), 'w') as f:
         f.write('iter,train_auroc,train_aupr,test_auroc,test_aupr\n')
@@ -245,6 +256,4 @@ def train(args, dataset, cv):
         best_model.load_state_dict(th.load(os.path.join(args.save_dir, 'best_model_fold%s.pth' % args.save_id)))
         top = get_top_novel_predictions(args, best_model, dataset, cv, top_k=args.top_k)
         print('Top 5 novel predictions:\n%s' % top.head(5))
-    if entry_stream is not None:
-        th.cuda.set_stream(entry_stream)           # leave the caller's stream current again
     return best['auroc'], best['aupr']

@@ -316,3 +316,19 @@ def test_chunked_spmm_composition_with_a_stand_in_kernel(monkeypatch):
     assert [c[0] for c in calls[1:]] == [n_rows + nnz // 16, n_rows] and calls[1][1] & ops.SPMM_RELU == 0
     assert th.equal(one, two) and csr._plan is not None
     assert th.equal(ops._spmm_raw(csr, x, ss, ds, bias, ops.SPMM_RELU), one) and len(calls) == 5       # cached plan
+
+
+def test_zipf_cells_stress_set_generator():
+    """synthetic.zipf_cells (secondary stress set): distinct in-range cells, seeded, with the popular
+    drugs saturated at every disease and a long tail of short rows."""
+    from dreamgnn_b200 import synthetic
+    n_d, n_s = 2000, 300
+    draw = lambda seed: synthetic.zipf_cells(n_d, n_s, 400_000, th.Generator().manual_seed(seed), 'cpu')
+    cells = draw(5)
+    assert th.equal(cells, draw(5)) and not th.equal(cells, draw(6))
+    assert th.equal(cells, th.unique(cells)) and 0 <= int(cells.min()) and int(cells.max()) < n_d * n_s
+    deg = th.bincount(cells // n_s, minlength=n_d)
+    assert int(deg.max()) == n_s and int((deg == n_s).sum()) >= 5          # the head saturates
+    assert float(deg.float().median()) < 0.2 * n_s                         # the tail is short
+    spec = dict(synthetic.SHAPES['syn20m'], pair_dist='zipf')
+    assert synthetic.scaled(spec, 0.5)['pair_dist'] == 'zipf'              # the option survives scaling
