@@ -226,7 +226,7 @@ def test_spmm_chunked_aggregation_of_skewed_rows(dev, d, weighted, scaled, epi):
     plain.split_T = 0
     plain.transpose().split_T = 0
     one = o.spmm(plain, xg.detach(), to(ss), to(ds), None if bg is None else bg.detach(), relu=epi)
-    assert plain._plan is None and H.rel_err(out.detach().cpu(), one.cpu()) <= 2e-6
+    assert plain._plan is None and H.rel_err(out.detach().cpu(), one.cpu()) <= 5e-6
     # a dropout compaction keeps the decision in both orientations
     flags = th.ones(e, dtype=th.uint8, device=dev)
     dropped = o.csr_dropout(csr, flags, e)
