@@ -698,6 +698,19 @@ def run_b200(args):
             import traceback
             traceback.print_exc()
             out['cv_jobs'] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:300])}
+    if world == 1 and args.workload == 'syn20m' and args.scale == 1.0 and not args.no_extra:
+        # the hot kernels against the library kernels of a stock PyTorch / DGL GPU path, same box, same inputs
+        try:
+            import importlib.util
+            th.cuda.empty_cache()
+            sp = importlib.util.spec_from_file_location('dg_library_compare', os.path.join(REPO, 'scripts', 'library_compare.py'))
+            mod = importlib.util.module_from_spec(sp)
+            sp.loader.exec_module(mod)
+            out['vs_library'] = mod.bench_block(ctx.dev)
+        except Exception as e:                                   # noqa: BLE001 -- never lose the main line
+            import traceback
+            traceback.print_exc()
+            out['vs_library'] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:300] if str(e) else '')}
     if rank == 0:
         emit(out)
     if world > 1:

@@ -172,12 +172,51 @@ def gemm_compare(out, reps, gen, dev):
     ref = x.double() @ w.double()
     out(impl='dg_gemm_f32 (3xTF32, tcgen05)', TFLOPs_fp32_equiv=round(2 * m * k * n / own['min_ms'] / 1e9, 1),
         rel_err_vs_f64=rel(ops.gemm(x, w, trans_b=True), ref), **base, **own)
+    was = th.backends.cuda.matmul.allow_tf32
     for tf32 in (False, True):
         th.backends.cuda.matmul.allow_tf32 = tf32
         t = timeit(lambda: th.mm(x, w), reps)
         out(impl='torch.mm (cuBLAS, %s)' % ('TF32 allowed' if tf32 else 'strict fp32'), speedup_own=round(t['min_ms'] / own['min_ms'], 2),
             rel_err_vs_f64=rel(th.mm(x, w), ref), **base, **t)
-    th.backends.cuda.matmul.allow_tf32 = False
+    th.backends.cuda.matmul.allow_tf32 = was
+
+
+def bench_block(dev, pairs=20_000_000, n_d=100_000, n_s=50_000, reps=3):
+    """The short form bench.py adds to its line as `vs_library` (kernels alone, CUDA events, same inputs, this box): the
+    d=344 relation-block SpMM against cuSPARSE, the projection GEMM against cuBLAS, the decoder forward against torch."""
+    rows = []
+    out = lambda **kw: rows.append(kw)
+    gen = th.Generator(dev).manual_seed(1234)
+    cells = th.unique(th.randint(0, n_d * n_s, (pairs,), generator=gen, device=dev))
+    lab = (th.rand(cells.numel(), generator=gen, device=dev) < 0.01)
+    order = th.argsort(lab.float(), descending=True, stable=True)
+    cells, lab = cells[order], lab[order].int()
+    drug, dis = (cells // n_s).int(), (cells % n_s).int()
+    del cells, order
+    by_dis = relation_block(dis, drug, lab, n_s, n_d)
+    guarded(out, 'spmm', lambda: spmm_compare(out, 'uniform, dst=disease', by_dis, 344, reps, gen, False))
+    del by_dis
+    guarded(out, 'gemm', lambda: gemm_compare(out, reps, gen, dev))
+
+    def dec():
+        mk = lambda *s_: th.randn(*s_, device=dev, generator=gen) * 0.3
+        pd, ps, w2, b2, w3, b3 = mk(n_d, 128), mk(n_s, 128), mk(64, 128), mk(64), mk(1, 64), mk(1)
+        pg = ops.PairGraph(drug, dis, n_d, n_s)
+        sl, dl = drug.long(), dis.long()
+        lin = th.nn.functional.linear
+        with th.no_grad():
+            own = timeit(lambda: ops.decoder_mlp(pd, ps, w2, b2, w3, b3, pg), reps)
+            lib = timeit(lambda: lin(th.relu(lin(th.relu(pd[sl] + ps[dl]), w2, b2)), w3, b3), reps)
+        out(what='decoder forward', pairs=int(drug.numel()), impl='dg_decoder_fwd_f32', **own)
+        out(what='decoder forward', pairs=int(drug.numel()), impl='torch gather + F.linear (split lin1)',
+            speedup_own=round(lib['min_ms'] / own['min_ms'], 2), **lib)
+    guarded(out, 'decoder', dec)
+    th.cuda.empty_cache()
+    keep = ('what', 'impl', 'graph', 'd', 'nnz', 'pairs', 'M', 'K', 'N', 'min_ms', 'median_ms', 'speedup_own', 'gather_TBps',
+            'TFLOPs_fp32_equiv', 'rel_err_vs_f64', 'own_vs_library_rel_err', 'error')
+    return {'how': 'kernels alone after a warm-up, CUDA events, minimum / median of %d, same inputs on this box; speedup_own = '
+                   'library time / own time (scripts/library_compare.py; full tables: profiles/r02c_library_compare.md)' % reps,
+            'rows': [{k: r[k] for k in keep if k in r} for r in rows]}
 
 
 def main():
